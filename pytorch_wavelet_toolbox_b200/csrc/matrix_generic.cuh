@@ -1,0 +1,143 @@
+// matrix_generic.cuh -- one level of the boundary-filter matrix FWT (general path).
+//
+// The reference multiplies by a sparse n x n operator (torch.sparse.mm,
+// src/ptwt/matmul_transform.py:422 and :688).  That operator is a stride-2 filter band
+// ("sameshift" rows of the convolution matrix, src/ptwt/sparse_math.py:371-377, :503-505)
+// whose truncated first / last rows have been replaced by QR-orthogonalised dense rows
+// (src/ptwt/sparse_math.py:253-311).  Here the band is applied as a filter and the
+// replaced rows as small dense blocks; nothing n x n is ever materialised.
+#pragma once
+
+#include "common.cuh"
+
+namespace wtb {
+
+template <typename T>
+struct MatFwdParams {
+    const T* x;  // [batch, n_in]
+    T* lo;       // [batch, n/2]
+    T* hi;
+    int64_t batch, n, n_in, x_stride, lo_stride, hi_stride;
+    int L, shift, odd_mode;
+    int nb_top, nb_bot, w_top, w_bot;
+    const T* lo_top;
+    const T* lo_bot;
+    const T* hi_top;
+    const T* hi_bot;
+    Taps<T> taps;  // un-flipped dec_lo / dec_hi
+};
+
+template <typename T>
+__device__ __forceinline__ T mat_sample(const T* __restrict__ xb, int64_t c, int64_t n_in, int odd_mode) {
+    if (c < n_in) return __ldg(xb + c);
+    // the single appended sample of an odd-length level input
+    // (F.pad(..., (0, 1), mode), reference matmul_transform.py:381-388, :412-421)
+    switch (odd_mode) {
+        case WT_MODE_ZERO: return T(0);
+        case WT_MODE_REFLECT: return __ldg(xb + (n_in >= 2 ? n_in - 2 : 0));
+        case WT_MODE_PERIODIC: return __ldg(xb);
+        default: return __ldg(xb + n_in - 1);  // constant, symmetric
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) mat_fwd_kernel(const __grid_constant__ MatFwdParams<T> p) {
+    const int64_t half = p.n / 2;
+    const int64_t total = p.batch * half;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx % half;
+        const int64_t b = idx / half;
+        const T* __restrict__ xb = p.x + b * p.x_stride;
+        T alo = T(0), ahi = T(0);
+        if (i < p.nb_top) {
+            const T* __restrict__ rl = p.lo_top + i * p.w_top;
+            const T* __restrict__ rh = p.hi_top + i * p.w_top;
+            for (int c = 0; c < p.w_top; ++c) {
+                const T v = mat_sample(xb, (int64_t)c, p.n_in, p.odd_mode);
+                alo = fma(__ldg(rl + c), v, alo);
+                ahi = fma(__ldg(rh + c), v, ahi);
+            }
+        } else if (i >= half - p.nb_bot) {
+            const int64_t r = i - (half - p.nb_bot);
+            const T* __restrict__ rl = p.lo_bot + r * p.w_bot;
+            const T* __restrict__ rh = p.hi_bot + r * p.w_bot;
+            const int64_t c0 = p.n - p.w_bot;
+            for (int c = 0; c < p.w_bot; ++c) {
+                const T v = mat_sample(xb, c0 + c, p.n_in, p.odd_mode);
+                alo = fma(__ldg(rl + c), v, alo);
+                ahi = fma(__ldg(rh + c), v, ahi);
+            }
+        } else {
+            const int64_t top = 2 * i + p.shift;  // column hit by tap 0
+            for (int m = 0; m < p.L; ++m) {
+                const int64_t c = top - m;
+                if (c < 0 || c >= p.n) continue;
+                const T v = mat_sample(xb, c, p.n_in, p.odd_mode);
+                alo = fma(p.taps.lo[m], v, alo);
+                ahi = fma(p.taps.hi[m], v, ahi);
+            }
+        }
+        p.lo[b * p.lo_stride + i] = alo;
+        p.hi[b * p.hi_stride + i] = ahi;
+    }
+}
+
+template <typename T>
+struct MatInvParams {
+    const T* lo;  // [batch, n/2]
+    const T* hi;
+    T* y;         // [batch, keep]
+    int64_t batch, n, keep, lo_stride, hi_stride, y_stride;
+    int L, shift;
+    int nb_top, nb_bot, w_top, w_bot;
+    const T* lo_top;
+    const T* lo_bot;
+    const T* hi_top;
+    const T* hi_bot;
+    Taps<T> taps;  // FLIPPED rec_lo / rec_hi (rows of S^T, reference matmul_transform.py:110-116)
+};
+
+// y = S [lo; hi] with S^T rows = stride-2 band of the flipped reconstruction filters,
+// boundary rows replaced by the dense blocks.
+template <typename T>
+__global__ void __launch_bounds__(256) mat_inv_kernel(const __grid_constant__ MatInvParams<T> p) {
+    const int64_t half = p.n / 2;
+    const int64_t total = p.batch * p.keep;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = idx % p.keep;
+        const int64_t b = idx / p.keep;
+        const T* __restrict__ lb = p.lo + b * p.lo_stride;
+        const T* __restrict__ hb = p.hi + b * p.hi_stride;
+        T acc = T(0);
+        // interior rows: tap m = 2 i + shift - t in [0, L)
+        int64_t i0 = (t - p.shift + 1) >> 1;  // ceil((t - shift) / 2)
+        int64_t i1 = (t - p.shift + p.L - 1) >> 1;
+        if (i0 < p.nb_top) i0 = p.nb_top;
+        if (i1 > half - p.nb_bot - 1) i1 = half - p.nb_bot - 1;
+        for (int64_t i = i0; i <= i1; ++i) {
+            const int m = (int)(2 * i + p.shift - t);
+            acc = fma(p.taps.lo[m], __ldg(lb + i), acc);
+            acc = fma(p.taps.hi[m], __ldg(hb + i), acc);
+        }
+        if (t < p.w_top) {
+            for (int r = 0; r < p.nb_top; ++r) {
+                acc = fma(__ldg(p.lo_top + r * p.w_top + t), __ldg(lb + r), acc);
+                acc = fma(__ldg(p.hi_top + r * p.w_top + t), __ldg(hb + r), acc);
+            }
+        }
+        const int64_t c0 = p.n - p.w_bot;
+        if (t >= c0) {
+            const int64_t c = t - c0;
+            for (int r = 0; r < p.nb_bot; ++r) {
+                const int64_t i = half - p.nb_bot + r;
+                acc = fma(__ldg(p.lo_bot + r * p.w_bot + c), __ldg(lb + i), acc);
+                acc = fma(__ldg(p.hi_bot + r * p.w_bot + c), __ldg(hb + i), acc);
+            }
+        }
+        p.y[b * p.y_stride + t] = acc;
+    }
+}
+
+}  // namespace wtb

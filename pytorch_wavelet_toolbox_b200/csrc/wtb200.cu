@@ -1,0 +1,613 @@
+// wtb200.cu -- C ABI (include/wtb200.h) and host-side drivers of the B200 wavelet
+// filter bank.  Build: see build.py (nvcc -gencode arch=compute_100a,code=sm_100a).
+//
+// Host drivers here only sequence launches; they never allocate device memory, never
+// synchronise, and keep no state besides the launch counter and the thread-local error
+// string.
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+#include "generic_axis.cuh"
+#include "matrix_generic.cuh"
+#ifndef WTB_NO_FUSED
+#include "fused2d.cuh"
+#endif
+
+namespace wtb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+}
+
+static inline int pad_left(int L) { return (2 * L - 3) / 2; }
+
+static inline int64_t coeff_len(int64_t n, int L) {
+    // F.pad by (padl, padl + n%2) then a stride-2 valid convolution with L taps
+    // (reference src/ptwt/_util.py:222-228).
+    const int64_t padl = pad_left(L);
+    const int64_t padded = n + 2 * padl + (n % 2);
+    return (padded - L) / 2 + 1;
+}
+
+static int grid_for(int64_t total, int block) {
+    int64_t g = (total + block - 1) / block;
+    const int64_t cap = 148LL * 64;  // grid-stride beyond this
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+template <typename T>
+static void fill_taps(Taps<T>& t, const double* lo, const double* hi, int L, bool flip) {
+    for (int k = 0; k < L; ++k) {
+        const int s = flip ? L - 1 - k : k;
+        t.lo[k] = (T)lo[s];
+        t.hi[k] = (T)hi[s];
+    }
+}
+
+// ---- one single-axis pass over a [o1, o2, n, inner] view -------------------------------
+template <typename T>
+struct View {
+    T* ptr;
+    int64_t s_o1, s_o2, s_n;
+};
+
+template <typename T>
+static cudaError_t launch_axis_fwd(const View<const T>& x, const View<T>& lo, const View<T>& hi,
+                                   int64_t o1, int64_t o2, int64_t n, int64_t inner, int mode, int L,
+                                   const Taps<T>& taps, cudaStream_t st) {
+    AxisFwdParams<T> p;
+    p.x = x.ptr; p.lo = lo.ptr; p.hi = hi.ptr;
+    p.n = n; p.m = coeff_len(n, L); p.inner = inner; p.o1 = o1; p.o2 = o2;
+    p.xs_o1 = x.s_o1; p.xs_o2 = x.s_o2; p.xs_n = x.s_n;
+    p.ls_o1 = lo.s_o1; p.ls_o2 = lo.s_o2; p.ls_m = lo.s_n;
+    p.hs_o1 = hi.s_o1; p.hs_o2 = hi.s_o2; p.hs_m = hi.s_n;
+    p.mode = mode; p.L = L; p.padl = pad_left(L);
+    p.taps = taps;
+    const int64_t total = o1 * o2 * p.m * inner;
+    if (total == 0) return cudaSuccess;
+    axis_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+template <typename T>
+static cudaError_t launch_axis_inv(const View<const T>& lo, const View<const T>& hi, const View<T>& y,
+                                   int64_t o1, int64_t o2, int64_t m, int64_t nout, int64_t inner, int L,
+                                   const Taps<T>& taps, cudaStream_t st) {
+    AxisInvParams<T> p;
+    p.lo = lo.ptr; p.hi = hi.ptr; p.y = y.ptr;
+    p.m = m; p.nout = nout; p.inner = inner; p.o1 = o1; p.o2 = o2;
+    p.ls_o1 = lo.s_o1; p.ls_o2 = lo.s_o2; p.ls_m = lo.s_n;
+    p.hs_o1 = hi.s_o1; p.hs_o2 = hi.s_o2; p.hs_m = hi.s_n;
+    p.ys_o1 = y.s_o1; p.ys_o2 = y.s_o2; p.ys_n = y.s_n;
+    p.L = L; p.padl = pad_left(L);
+    p.taps = taps;
+    const int64_t total = o1 * o2 * nout * inner;
+    if (total == 0) return cudaSuccess;
+    axis_inv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+// Scratch layout of the general (one launch per axis pass) path, in elements.
+static void generic_scratch_elems(int ndim, int L, int64_t batch, const int64_t* dims, int inverse,
+                                  int64_t* s1, int64_t* s2) {
+    *s1 = 0; *s2 = 0;
+    if (ndim == 1) return;
+    if (!inverse) {
+        if (ndim == 2) {
+            *s1 = 2 * batch * dims[0] * coeff_len(dims[1], L);
+        } else {
+            *s1 = 2 * batch * dims[0] * dims[1] * coeff_len(dims[2], L);
+            *s2 = 4 * batch * dims[0] * coeff_len(dims[1], L) * coeff_len(dims[2], L);
+        }
+    } else {
+        // dims = extents of the finest reconstruction (upper bound for every level)
+        int64_t c[3];
+        for (int a = 0; a < ndim; ++a) c[a] = coeff_len(dims[a] + (dims[a] & 1), L) + 1;
+        int64_t full[3];
+        for (int a = 0; a < ndim; ++a) full[a] = dims[a] + 1;
+        if (ndim == 2) {
+            *s1 = 2 * batch * full[0] * c[1];
+        } else {
+            *s1 = 4 * batch * full[0] * c[1] * c[2];
+            *s2 = 2 * batch * full[0] * full[1] * c[2];
+        }
+    }
+}
+
+template <typename T>
+static int dwt_fwd_generic(int ndim, int mode, int levels, int L, const Taps<T>& taps, const T* x,
+                           int64_t batch, const int64_t* dims, const int64_t* xs, int64_t xbs,
+                           const wt_level* lv, int first_level, T* ws, cudaStream_t st) {
+    int64_t cur[3];
+    int64_t cs[3];
+    int64_t cbs = xbs;
+    const T* src = x;
+    for (int a = 0; a < ndim; ++a) { cur[a] = dims[a]; cs[a] = xs[a]; }
+    for (int l = 0; l < first_level; ++l) {
+        // skip levels already done by a specialised kernel
+        src = (const T*)lv[l].approx; cbs = lv[l].approx_batch_stride;
+        for (int a = 0; a < ndim; ++a) { cur[a] = lv[l].dims[a]; cs[a] = lv[l].approx_strides[a]; }
+    }
+    for (int l = first_level; l < levels; ++l) {
+        const wt_level& d = lv[l];
+        T* det = (T*)d.details;
+        T* app = (T*)d.approx;
+        // output band k as a view: s_o1 = batch stride; st(k)[a] = element stride of axis a
+        auto band = [&](int k) -> View<T> {
+            if (k == 0) return View<T>{app, d.approx_batch_stride, 0, 0};
+            return View<T>{det + (int64_t)(k - 1) * d.band_stride, d.details_batch_stride, 0, 0};
+        };
+        auto st_of = [&](int k) -> const int64_t* { return k == 0 ? d.approx_strides : d.strides; };
+        cudaError_t e = cudaSuccess;
+        if (ndim == 1) {
+            View<const T> xv{src, cbs, 0, cs[0]};
+            View<T> lo = band(0), hi = band(1);
+            lo.s_n = st_of(0)[0]; hi.s_n = st_of(1)[0];
+            e = launch_axis_fwd<T>(xv, lo, hi, batch, 1, cur[0], 1, mode, L, taps, st);
+            if (e != cudaSuccess) return cuda_fail(e, "axis_fwd_kernel");
+        } else if (ndim == 2) {
+            const int64_t H = cur[0], W = cur[1], Mw = d.dims[1];
+            T* tlo = ws;
+            T* thi = ws + batch * H * Mw;
+            // pass along W (last axis): [batch, H, W] -> t{lo,hi} [batch, H, Mw]
+            if (cs[1] != 1) return fail(WT_EINVAL, "innermost stride must be 1");
+            {
+                View<const T> xv{src, cbs, cs[0], 1};
+                View<T> lo{tlo, H * Mw, Mw, 1}, hi{thi, H * Mw, Mw, 1};
+                e = launch_axis_fwd<T>(xv, lo, hi, batch, H, W, 1, mode, L, taps, st);
+                if (e != cudaSuccess) return cuda_fail(e, "axis_fwd_kernel(W)");
+            }
+            // pass along H: t_lo -> (k=0, k=2), t_hi -> (k=1, k=3)
+            for (int w = 0; w < 2; ++w) {
+                View<const T> xv{w ? thi : tlo, H * Mw, 0, Mw};
+                View<T> lo = band(w), hi = band(2 + w);
+                lo.s_n = st_of(w)[0]; hi.s_n = st_of(2 + w)[0];
+                if (st_of(w)[1] != 1 || st_of(2 + w)[1] != 1) return fail(WT_EINVAL, "innermost stride must be 1");
+                e = launch_axis_fwd<T>(xv, lo, hi, batch, 1, H, Mw, mode, L, taps, st);
+                if (e != cudaSuccess) return cuda_fail(e, "axis_fwd_kernel(H)");
+            }
+        } else {
+            const int64_t D = cur[0], H = cur[1], W = cur[2];
+            const int64_t Mh = d.dims[1], Mw = d.dims[2];
+            if (cs[2] != 1 || d.strides[2] != 1 || d.approx_strides[2] != 1)
+                return fail(WT_EINVAL, "innermost stride must be 1");
+            const int64_t n1 = batch * D * H * Mw;
+            T* t1[2] = {ws, ws + n1};
+            const int64_t n2 = batch * D * Mh * Mw;
+            T* t2base = ws + 2 * n1;
+            // W pass: view [batch*?]: o1 = batch, o2 = D*H needs uniform stride -> do per (batch, D) x H rows
+            // input [batch, D, H, W]: o1 = batch (stride cbs), o2 = D (stride cs[0]) with rows H folded
+            // into n-major is not possible in one view, so fold (D, H) when contiguous, else loop D.
+            if (cs[0] == H * cs[1]) {
+                View<const T> xv{src, cbs, cs[1], 1};
+                View<T> lo{t1[0], D * H * Mw, Mw, 1}, hi{t1[1], D * H * Mw, Mw, 1};
+                e = launch_axis_fwd<T>(xv, lo, hi, batch, D * H, W, 1, mode, L, taps, st);
+                if (e != cudaSuccess) return cuda_fail(e, "axis_fwd_kernel(W)");
+            } else {
+                for (int64_t z = 0; z < D; ++z) {
+                    View<const T> xv{src + z * cs[0], cbs, cs[1], 1};
+                    View<T> lo{t1[0] + z * H * Mw, D * H * Mw, Mw, 1}, hi{t1[1] + z * H * Mw, D * H * Mw, Mw, 1};
+                    e = launch_axis_fwd<T>(xv, lo, hi, batch, H, W, 1, mode, L, taps, st);
+                    if (e != cudaSuccess) return cuda_fail(e, "axis_fwd_kernel(W)");
+                }
+            }
+            // H pass: t1[w] [batch*D, H, Mw] -> t2[h][w] [batch*D, Mh, Mw]
+            for (int w = 0; w < 2; ++w) {
+                View<const T> xv{t1[w], H * Mw, 0, Mw};
+                View<T> lo{t2base + (0 * 2 + w) * n2, Mh * Mw, 0, Mw};
+                View<T> hi{t2base + (1 * 2 + w) * n2, Mh * Mw, 0, Mw};
+                e = launch_axis_fwd<T>(xv, lo, hi, batch * D, 1, H, Mw, mode, L, taps, st);
+                if (e != cudaSuccess) return cuda_fail(e, "axis_fwd_kernel(H)");
+            }
+            // D pass: t2[h][w] [batch, D, Mh*Mw] -> bands k = 4 d + 2 h + w, inner = Mh*Mw needs the
+            // output plane to be dense: out stride[0] == Mh * stride[1] and stride[1] == Mw ... general
+            // case: treat inner = Mw rows and o2 = Mh.
+            for (int hw = 0; hw < 4; ++hw) {
+                View<const T> xv{t2base + hw * n2, D * Mh * Mw, Mw, Mh * Mw};
+                View<T> lo = band(hw), hi = band(4 + hw);
+                lo.s_o2 = st_of(hw)[1]; hi.s_o2 = st_of(4 + hw)[1];
+                lo.s_n = st_of(hw)[0]; hi.s_n = st_of(4 + hw)[0];
+                e = launch_axis_fwd<T>(xv, lo, hi, batch, Mh, D, Mw, mode, L, taps, st);
+                if (e != cudaSuccess) return cuda_fail(e, "axis_fwd_kernel(D)");
+            }
+        }
+        src = app; cbs = d.approx_batch_stride;
+        for (int a = 0; a < ndim; ++a) { cur[a] = d.dims[a]; cs[a] = d.approx_strides[a]; }
+    }
+    return 0;
+}
+
+template <typename T>
+static int dwt_inv_generic(int ndim, int levels, int L, const Taps<T>& taps, T* y, int64_t batch,
+                           const int64_t* out_dims, const int64_t* ys, int64_t ybs, const wt_level* lv,
+                           int last_level, T* ws, cudaStream_t st) {
+    // last_level: levels [levels-1 .. last_level] are processed here (last_level = 0 -> all)
+    for (int l = levels - 1; l >= last_level; --l) {
+        const wt_level& d = lv[l];
+        const T* det = (const T*)d.details;
+        const T* app = (const T*)d.approx;
+        auto band = [&](int k) -> View<const T> {
+            if (k == 0) return View<const T>{app, d.approx_batch_stride, 0, 0};
+            return View<const T>{det + (int64_t)(k - 1) * d.band_stride, d.details_batch_stride, 0, 0};
+        };
+        auto st_of = [&](int k) -> const int64_t* { return k == 0 ? d.approx_strides : d.strides; };
+        // destination of this level's reconstruction
+        T* dst; int64_t dbs; int64_t ds[3]; int64_t dd[3];
+        if (l > 0) {
+            dst = (T*)lv[l - 1].approx; dbs = lv[l - 1].approx_batch_stride;
+            for (int a = 0; a < ndim; ++a) { ds[a] = lv[l - 1].approx_strides[a]; dd[a] = lv[l - 1].dims[a]; }
+        } else {
+            dst = y; dbs = ybs;
+            for (int a = 0; a < ndim; ++a) { ds[a] = ys[a]; dd[a] = out_dims[a]; }
+        }
+        cudaError_t e = cudaSuccess;
+        if (ndim == 1) {
+            View<const T> lo = band(0), hi = band(1);
+            lo.s_n = st_of(0)[0]; hi.s_n = st_of(1)[0];
+            View<T> yv{dst, dbs, 0, ds[0]};
+            e = launch_axis_inv<T>(lo, hi, yv, batch, 1, d.dims[0], dd[0], 1, L, taps, st);
+            if (e != cudaSuccess) return cuda_fail(e, "axis_inv_kernel");
+        } else if (ndim == 2) {
+            const int64_t Mh = d.dims[0], Mw = d.dims[1], OH = dd[0], OW = dd[1];
+            if (d.strides[1] != 1 || d.approx_strides[1] != 1 || ds[1] != 1)
+                return fail(WT_EINVAL, "innermost stride must be 1");
+            T* t[2] = {ws, ws + batch * OH * Mw};
+            // along H: (k=0,k=2) -> t_lo ; (k=1,k=3) -> t_hi    [batch, OH, Mw]
+            for (int w = 0; w < 2; ++w) {
+                View<const T> lo = band(w), hi = band(2 + w);
+                lo.s_n = st_of(w)[0]; hi.s_n = st_of(2 + w)[0];
+                View<T> yv{t[w], OH * Mw, 0, Mw};
+                e = launch_axis_inv<T>(lo, hi, yv, batch, 1, Mh, OH, Mw, L, taps, st);
+                if (e != cudaSuccess) return cuda_fail(e, "axis_inv_kernel(H)");
+            }
+            // along W
+            View<const T> lo{t[0], OH * Mw, Mw, 1}, hi{t[1], OH * Mw, Mw, 1};
+            View<T> yv{dst, dbs, ds[0], 1};
+            e = launch_axis_inv<T>(lo, hi, yv, batch, OH, Mw, OW, 1, L, taps, st);
+            if (e != cudaSuccess) return cuda_fail(e, "axis_inv_kernel(W)");
+        } else {
+            const int64_t Md = d.dims[0], Mh = d.dims[1], Mw = d.dims[2];
+            const int64_t OD = dd[0], OH = dd[1], OW = dd[2];
+            if (d.strides[2] != 1 || d.approx_strides[2] != 1 || ds[2] != 1)
+                return fail(WT_EINVAL, "innermost stride must be 1");
+            const int64_t n1 = batch * OD * Mh * Mw;
+            T* t1 = ws;                 // 4 arrays [batch, OD, Mh, Mw]
+            T* t2 = ws + 4 * n1;        // 2 arrays [batch, OD, OH, Mw]
+            const int64_t n2 = batch * OD * OH * Mw;
+            for (int hw = 0; hw < 4; ++hw) {
+                View<const T> lo = band(hw), hi = band(4 + hw);
+                lo.s_o2 = st_of(hw)[1]; hi.s_o2 = st_of(4 + hw)[1];
+                lo.s_n = st_of(hw)[0]; hi.s_n = st_of(4 + hw)[0];
+                View<T> yv{t1 + hw * n1, OD * Mh * Mw, Mw, Mh * Mw};
+                e = launch_axis_inv<T>(lo, hi, yv, batch, Mh, Md, OD, Mw, L, taps, st);
+                if (e != cudaSuccess) return cuda_fail(e, "axis_inv_kernel(D)");
+            }
+            for (int w = 0; w < 2; ++w) {
+                View<const T> lo{t1 + (0 * 2 + w) * n1, Mh * Mw, 0, Mw}, hi{t1 + (1 * 2 + w) * n1, Mh * Mw, 0, Mw};
+                View<T> yv{t2 + w * n2, OH * Mw, 0, Mw};
+                e = launch_axis_inv<T>(lo, hi, yv, batch * OD, 1, Mh, OH, Mw, L, taps, st);
+                if (e != cudaSuccess) return cuda_fail(e, "axis_inv_kernel(H)");
+            }
+            if (ds[0] == OH * ds[1]) {
+                View<const T> lo{t2, OD * OH * Mw, Mw, 1}, hi{t2 + n2, OD * OH * Mw, Mw, 1};
+                View<T> yv{dst, dbs, ds[1], 1};
+                e = launch_axis_inv<T>(lo, hi, yv, batch, OD * OH, Mw, OW, 1, L, taps, st);
+                if (e != cudaSuccess) return cuda_fail(e, "axis_inv_kernel(W)");
+            } else {
+                for (int64_t z = 0; z < OD; ++z) {
+                    View<const T> lo{t2 + z * OH * Mw, OD * OH * Mw, Mw, 1}, hi{t2 + n2 + z * OH * Mw, OD * OH * Mw, Mw, 1};
+                    View<T> yv{dst + z * ds[0], dbs, ds[1], 1};
+                    e = launch_axis_inv<T>(lo, hi, yv, batch, OH, Mw, OW, 1, L, taps, st);
+                    if (e != cudaSuccess) return cuda_fail(e, "axis_inv_kernel(W)");
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+static int check_common(int ndim, int dtype, int levels, int L, int64_t batch, const int64_t* dims) {
+    if (ndim < 1 || ndim > WT_MAX_NDIM) return fail(WT_EINVAL, "ndim must be 1..3, got %d", ndim);
+    if (dtype != WT_F32 && dtype != WT_F64) return fail(WT_EINVAL, "dtype must be WT_F32 or WT_F64");
+    if (levels < 0) return fail(WT_EINVAL, "levels must be >= 0");
+    if (L < 2 || L > WT_MAX_FILT_LEN) return fail(WT_EUNSUPPORTED, "filter length %d outside [2, %d]", L, WT_MAX_FILT_LEN);
+    if (batch < 0) return fail(WT_EINVAL, "negative batch");
+    if (!dims) return fail(WT_EINVAL, "dims is NULL");
+    for (int a = 0; a < ndim; ++a)
+        if (dims[a] < 1) return fail(WT_ESHAPE, "extent %d is %lld", a, (long long)dims[a]);
+    return 0;
+}
+
+template <typename T>
+static int dwt_fwd_t(int ndim, int mode, int levels, int L, const double* dlo, const double* dhi,
+                     const void* x, int64_t batch, const int64_t* dims, const int64_t* xs, int64_t xbs,
+                     const wt_level* lv, void* ws, size_t ws_bytes, cudaStream_t st) {
+    Taps<T> taps;
+    fill_taps(taps, dlo, dhi, L, false);
+    // validate extents against the reference's formula
+    int64_t cur[3];
+    for (int a = 0; a < ndim; ++a) cur[a] = dims[a];
+    for (int l = 0; l < levels; ++l) {
+        for (int a = 0; a < ndim; ++a) {
+            const int64_t want = coeff_len(cur[a], L);
+            if (lv[l].dims[a] != want)
+                return fail(WT_ESHAPE, "level %d axis %d: extent %lld, expected %lld", l + 1, a,
+                            (long long)lv[l].dims[a], (long long)want);
+            cur[a] = want;
+        }
+        if (!lv[l].details || !lv[l].approx) return fail(WT_EINVAL, "level %d: NULL buffer", l + 1);
+    }
+    int64_t s1, s2;
+    generic_scratch_elems(ndim, L, batch, dims, 0, &s1, &s2);
+    int first_generic = 0;
+#ifndef WTB_NO_FUSED
+    {
+        int rc = fused2d_fwd_try<T>(ndim, mode, levels, L, dlo, dhi, (const T*)x, batch, dims, xs, xbs, lv,
+                                    st, &first_generic);
+        if (rc != 0) return rc;
+    }
+#endif
+    if (first_generic < levels) {
+        if (ndim > 1 && ((size_t)(s1 + s2) * sizeof(T) > ws_bytes || !ws))
+            return fail(WT_EWORKSPACE, "workspace: need %zu bytes, have %zu", (size_t)(s1 + s2) * sizeof(T), ws_bytes);
+        return dwt_fwd_generic<T>(ndim, mode, levels, L, taps, (const T*)x, batch, dims, xs, xbs, lv,
+                                  first_generic, (T*)ws, st);
+    }
+    return 0;
+}
+
+template <typename T>
+static int dwt_inv_t(int ndim, int levels, int L, const double* rlo, const double* rhi, void* y,
+                     int64_t batch, const int64_t* out_dims, const int64_t* ys, int64_t ybs,
+                     const wt_level* lv, void* ws, size_t ws_bytes, cudaStream_t st) {
+    Taps<T> taps;
+    fill_taps(taps, rlo, rhi, L, false);
+    const int padl = pad_left(L);
+    for (int l = levels - 1; l >= 0; --l) {
+        for (int a = 0; a < ndim; ++a) {
+            const int64_t full = 2 * (lv[l].dims[a] - 1) + L - 2 * padl;  // after the symmetric crop
+            const int64_t next = l > 0 ? lv[l - 1].dims[a] : out_dims[a];
+            if (!(next == full || next == full - 1))
+                return fail(WT_ESHAPE, "level %d axis %d: reconstruction has %lld samples, next level expects %lld",
+                            l + 1, a, (long long)full, (long long)next);
+        }
+        if (!lv[l].details || !lv[l].approx) return fail(WT_EINVAL, "level %d: NULL buffer", l + 1);
+    }
+    int64_t s1, s2;
+    generic_scratch_elems(ndim, L, batch, out_dims, 1, &s1, &s2);
+    if (ndim > 1 && levels > 0 && ((size_t)(s1 + s2) * sizeof(T) > ws_bytes || !ws))
+        return fail(WT_EWORKSPACE, "workspace: need %zu bytes, have %zu", (size_t)(s1 + s2) * sizeof(T), ws_bytes);
+    return dwt_inv_generic<T>(ndim, levels, L, taps, (T*)y, batch, out_dims, ys, ybs, lv, 0, (T*)ws, st);
+}
+
+// ---- matrix FWT -------------------------------------------------------------------------
+template <typename T>
+static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi, const int64_t* n,
+                        const int32_t* padded, int odd_mode, const int32_t* nbt, const int32_t* nbb,
+                        const int32_t* wt, const int32_t* wb, const void* blocks, const void* x, int64_t batch,
+                        int64_t xs, void* const* hi_out, const int64_t* hi_stride, void* lo_out,
+                        int64_t lo_stride, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    Taps<T> taps;
+    fill_taps(taps, dlo, dhi, L, false);
+    const size_t need = levels > 1 ? (size_t)2 * batch * (n[0] / 2) * sizeof(T) : 0;
+    if (need > scratch_bytes) return fail(WT_EWORKSPACE, "scratch: need %zu bytes, have %zu", need, scratch_bytes);
+    const T* blk = (const T*)blocks;
+    const T* src = (const T*)x;
+    int64_t src_stride = xs;
+    T* ping[2] = {(T*)scratch, (T*)scratch + batch * (n[0] / 2)};
+    for (int l = 0; l < levels; ++l) {
+        if (n[l] < 2 || (n[l] & 1)) return fail(WT_ESHAPE, "level %d: operator size %lld must be even", l + 1, (long long)n[l]);
+        MatFwdParams<T> p;
+        p.x = src; p.x_stride = src_stride;
+        p.batch = batch; p.n = n[l]; p.n_in = n[l] - (padded[l] ? 1 : 0);
+        p.hi = (T*)hi_out[l]; p.hi_stride = hi_stride[l];
+        const bool last = (l == levels - 1);
+        p.lo = last ? (T*)lo_out : ping[l & 1];
+        p.lo_stride = last ? lo_stride : n[l] / 2;
+        p.L = L; p.shift = L / 2 + (L % 2); p.odd_mode = odd_mode;
+        p.nb_top = nbt[l]; p.nb_bot = nbb[l]; p.w_top = wt[l]; p.w_bot = wb[l];
+        p.lo_top = blk; blk += (int64_t)nbt[l] * wt[l];
+        p.lo_bot = blk; blk += (int64_t)nbb[l] * wb[l];
+        p.hi_top = blk; blk += (int64_t)nbt[l] * wt[l];
+        p.hi_bot = blk; blk += (int64_t)nbb[l] * wb[l];
+        p.taps = taps;
+        const int64_t total = batch * (n[l] / 2);
+        if (total > 0) {
+            mat_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "mat_fwd_kernel");
+        }
+        src = p.lo; src_stride = p.lo_stride;
+    }
+    return 0;
+}
+
+template <typename T>
+static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi, const int64_t* n,
+                        const int64_t* next_len, const int32_t* nbt, const int32_t* nbb, const int32_t* wt,
+                        const int32_t* wb, const void* blocks, const void* lo_in, int64_t lo_stride,
+                        const void* const* hi_in, const int64_t* hi_stride, int64_t batch, void* y,
+                        int64_t ys, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    Taps<T> taps;
+    fill_taps(taps, rlo, rhi, L, true);  // rows of S^T carry the flipped rec filters
+    const size_t need = levels > 1 ? (size_t)2 * batch * n[0] * sizeof(T) : 0;
+    if (need > scratch_bytes) return fail(WT_EWORKSPACE, "scratch: need %zu bytes, have %zu", need, scratch_bytes);
+    // block offsets per level
+    int64_t off[64];
+    if (levels > 64) return fail(WT_EUNSUPPORTED, "more than 64 levels");
+    int64_t o = 0;
+    for (int l = 0; l < levels; ++l) {
+        off[l] = o;
+        o += 2 * ((int64_t)nbt[l] * wt[l] + (int64_t)nbb[l] * wb[l]);
+    }
+    const T* src = (const T*)lo_in;
+    int64_t src_stride = lo_stride;
+    T* ping[2] = {(T*)scratch, (T*)scratch + batch * n[0]};
+    for (int l = levels - 1; l >= 0; --l) {
+        MatInvParams<T> p;
+        p.lo = src; p.lo_stride = src_stride;
+        p.hi = (const T*)hi_in[l]; p.hi_stride = hi_stride[l];
+        p.batch = batch; p.n = n[l]; p.keep = next_len[l];
+        if (!(p.keep == p.n || p.keep == p.n - 1))
+            return fail(WT_ESHAPE, "level %d: keep %lld of %lld samples", l + 1, (long long)p.keep, (long long)p.n);
+        const bool last = (l == 0);
+        p.y = last ? (T*)y : ping[l & 1];
+        p.y_stride = last ? ys : p.keep;
+        p.L = L; p.shift = L / 2 + (L % 2);
+        p.nb_top = nbt[l]; p.nb_bot = nbb[l]; p.w_top = wt[l]; p.w_bot = wb[l];
+        const T* blk = (const T*)blocks + off[l];
+        p.lo_top = blk; blk += (int64_t)nbt[l] * wt[l];
+        p.lo_bot = blk; blk += (int64_t)nbb[l] * wb[l];
+        p.hi_top = blk; blk += (int64_t)nbt[l] * wt[l];
+        p.hi_bot = blk;
+        p.taps = taps;
+        const int64_t total = batch * p.keep;
+        if (total > 0) {
+            mat_inv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return cuda_fail(e, "mat_inv_kernel");
+        }
+        src = p.y; src_stride = p.y_stride;
+    }
+    return 0;
+}
+
+}  // namespace wtb
+
+using namespace wtb;
+
+extern "C" {
+
+int wt_version(void) { return WT_VERSION; }
+
+const char* wt_last_error(void) { return g_err; }
+
+int wt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceProperties");
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+int64_t wt_coeff_len(int64_t n, int filt_len) { return coeff_len(n, filt_len); }
+
+size_t wt_dwt_workspace_bytes(int ndim, int dtype, int levels, int filt_len, int64_t batch, const int64_t* dims,
+                              int inverse) {
+    if (ndim < 1 || ndim > 3 || !dims || levels <= 0) return 0;
+    int64_t s1, s2;
+    generic_scratch_elems(ndim, filt_len, batch, dims, inverse, &s1, &s2);
+    return (size_t)(s1 + s2) * (dtype == WT_F64 ? 8 : 4);
+}
+
+int wt_dwt_fwd(int ndim, int dtype, int mode, int levels, int filt_len, const double* dec_lo,
+               const double* dec_hi, const void* x, int64_t batch, const int64_t* dims, const int64_t* x_strides,
+               int64_t x_batch_stride, const wt_level* levels_desc, void* workspace, size_t workspace_bytes,
+               void* stream) {
+    int rc = check_common(ndim, dtype, levels, filt_len, batch, dims);
+    if (rc) return rc;
+    if (mode < WT_MODE_ZERO || mode > WT_MODE_SYMMETRIC) return fail(WT_EINVAL, "unknown boundary mode %d", mode);
+    if (!dec_lo || !dec_hi || !x_strides) return fail(WT_EINVAL, "NULL argument");
+    if (levels == 0 || batch == 0) return 0;
+    if (!x || !levels_desc) return fail(WT_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WT_F32)
+        return dwt_fwd_t<float>(ndim, mode, levels, filt_len, dec_lo, dec_hi, x, batch, dims, x_strides,
+                                x_batch_stride, levels_desc, workspace, workspace_bytes, st);
+    return dwt_fwd_t<double>(ndim, mode, levels, filt_len, dec_lo, dec_hi, x, batch, dims, x_strides,
+                             x_batch_stride, levels_desc, workspace, workspace_bytes, st);
+}
+
+int wt_dwt_inv(int ndim, int dtype, int levels, int filt_len, const double* rec_lo, const double* rec_hi,
+               void* y, int64_t batch, const int64_t* out_dims, const int64_t* y_strides, int64_t y_batch_stride,
+               const wt_level* levels_desc, void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(ndim, dtype, levels, filt_len, batch, out_dims);
+    if (rc) return rc;
+    if (!rec_lo || !rec_hi || !y_strides) return fail(WT_EINVAL, "NULL argument");
+    if (levels == 0 || batch == 0) return 0;
+    if (!y || !levels_desc) return fail(WT_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WT_F32)
+        return dwt_inv_t<float>(ndim, levels, filt_len, rec_lo, rec_hi, y, batch, out_dims, y_strides,
+                                y_batch_stride, levels_desc, workspace, workspace_bytes, st);
+    return dwt_inv_t<double>(ndim, levels, filt_len, rec_lo, rec_hi, y, batch, out_dims, y_strides,
+                             y_batch_stride, levels_desc, workspace, workspace_bytes, st);
+}
+
+int wt_matrix_fwd(int dtype, int levels, int filt_len, const double* dec_lo, const double* dec_hi,
+                  const int64_t* n, const int32_t* padded, int odd_mode, const int32_t* nb_top,
+                  const int32_t* nb_bot, const int32_t* w_top, const int32_t* w_bot, const void* blocks,
+                  const void* x, int64_t batch, int64_t x_stride, void* const* hi_out, const int64_t* hi_stride,
+                  void* lo_out, int64_t lo_stride, void* scratch, size_t scratch_bytes, void* stream) {
+    if (dtype != WT_F32 && dtype != WT_F64) return fail(WT_EINVAL, "dtype must be WT_F32 or WT_F64");
+    if (levels < 1) return fail(WT_EINVAL, "levels must be >= 1");
+    if (filt_len < 2 || filt_len > WT_MAX_FILT_LEN) return fail(WT_EUNSUPPORTED, "filter length %d", filt_len);
+    if (odd_mode < WT_MODE_ZERO || odd_mode > WT_MODE_SYMMETRIC) return fail(WT_EINVAL, "unknown padding mode %d", odd_mode);
+    if (!dec_lo || !dec_hi || !n || !padded || !nb_top || !nb_bot || !w_top || !w_bot || !hi_out || !hi_stride)
+        return fail(WT_EINVAL, "NULL argument");
+    if (batch == 0) return 0;
+    if (!x || !lo_out) return fail(WT_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WT_F32)
+        return matrix_fwd_t<float>(levels, filt_len, dec_lo, dec_hi, n, padded, odd_mode, nb_top, nb_bot, w_top,
+                                   w_bot, blocks, x, batch, x_stride, hi_out, hi_stride, lo_out, lo_stride,
+                                   scratch, scratch_bytes, st);
+    return matrix_fwd_t<double>(levels, filt_len, dec_lo, dec_hi, n, padded, odd_mode, nb_top, nb_bot, w_top,
+                                w_bot, blocks, x, batch, x_stride, hi_out, hi_stride, lo_out, lo_stride, scratch,
+                                scratch_bytes, st);
+}
+
+int wt_matrix_inv(int dtype, int levels, int filt_len, const double* rec_lo, const double* rec_hi,
+                  const int64_t* n, const int64_t* next_len, const int32_t* nb_top, const int32_t* nb_bot,
+                  const int32_t* w_top, const int32_t* w_bot, const void* blocks, const void* lo_in,
+                  int64_t lo_stride, const void* const* hi_in, const int64_t* hi_stride, int64_t batch, void* y,
+                  int64_t y_stride, void* scratch, size_t scratch_bytes, void* stream) {
+    if (dtype != WT_F32 && dtype != WT_F64) return fail(WT_EINVAL, "dtype must be WT_F32 or WT_F64");
+    if (levels < 1) return fail(WT_EINVAL, "levels must be >= 1");
+    if (filt_len < 2 || filt_len > WT_MAX_FILT_LEN) return fail(WT_EUNSUPPORTED, "filter length %d", filt_len);
+    if (!rec_lo || !rec_hi || !n || !next_len || !nb_top || !nb_bot || !w_top || !w_bot || !hi_in || !hi_stride)
+        return fail(WT_EINVAL, "NULL argument");
+    if (batch == 0) return 0;
+    if (!lo_in || !y) return fail(WT_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WT_F32)
+        return matrix_inv_t<float>(levels, filt_len, rec_lo, rec_hi, n, next_len, nb_top, nb_bot, w_top, w_bot,
+                                   blocks, lo_in, lo_stride, hi_in, hi_stride, batch, y, y_stride, scratch,
+                                   scratch_bytes, st);
+    return matrix_inv_t<double>(levels, filt_len, rec_lo, rec_hi, n, next_len, nb_top, nb_bot, w_top, w_bot,
+                                blocks, lo_in, lo_stride, hi_in, hi_stride, batch, y, y_stride, scratch,
+                                scratch_bytes, st);
+}
+
+uint64_t wt_launch_count(void) { return g_launches.load(); }
+void wt_launch_count_reset(void) { g_launches.store(0); }
+
+}  // extern "C"
