@@ -139,18 +139,20 @@ int wt_dwt_inv(int ndim, int dtype, int levels, int filt_len,
  *   padded[l]   1 if the level input had n[l]-1 samples and is extended by one sample
  *               using odd_mode (WT_MODE_*),
  *   nb_top[l], nb_bot[l]  number of orthogonalised boundary rows at the top / bottom of
- *               EACH half (lo and hi),
- *   w_top[l], w_bot[l]    column support of those rows (first w_top / last w_bot cols),
- *   blocks      device array, compute dtype; for each level in order: lo_top
- *               [nb_top x w_top], lo_bot [nb_bot x w_bot], hi_top, hi_bot (row-major).
- * x is [batch, n0] contiguous (n0 = n[0] - padded[0]).  hi_out[l] receives the detail
+ *               EACH half (lo and hi); nb = nb_top + nb_bot rows per half, top rows first,
+ *   w_left[l], w_right[l] column support of those rows: the first w_left and the last
+ *               w_right columns (the QR leaves round-off sized entries of a top row in the
+ *               right corner and vice versa; they are kept, like the reference keeps them),
+ *   blocks      device array, compute dtype; for each level in order: lo_left
+ *               [nb x w_left], lo_right [nb x w_right], hi_left, hi_right (row-major).
+ * x is [batch, n0] contiguous rows (n0 = n[0] - padded[0]).  hi_out[l] receives the detail
  * of level l ([batch, n[l]/2], row stride hi_stride[l]); lo_out the coarsest approximation.
  * scratch must hold 2 * batch * (n[0]/2) elements. */
 int wt_matrix_fwd(int dtype, int levels, int filt_len,
                   const double* dec_lo, const double* dec_hi,
                   const int64_t* n, const int32_t* padded, int odd_mode,
                   const int32_t* nb_top, const int32_t* nb_bot,
-                  const int32_t* w_top, const int32_t* w_bot, const void* blocks,
+                  const int32_t* w_left, const int32_t* w_right, const void* blocks,
                   const void* x, int64_t batch, int64_t x_stride,
                   void* const* hi_out, const int64_t* hi_stride,
                   void* lo_out, int64_t lo_stride,
@@ -165,7 +167,7 @@ int wt_matrix_inv(int dtype, int levels, int filt_len,
                   const double* rec_lo, const double* rec_hi,
                   const int64_t* n, const int64_t* next_len,
                   const int32_t* nb_top, const int32_t* nb_bot,
-                  const int32_t* w_top, const int32_t* w_bot, const void* blocks,
+                  const int32_t* w_left, const int32_t* w_right, const void* blocks,
                   const void* lo_in, int64_t lo_stride,
                   const void* const* hi_in, const int64_t* hi_stride,
                   int64_t batch, void* y, int64_t y_stride,

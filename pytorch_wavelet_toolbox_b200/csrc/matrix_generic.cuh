@@ -19,11 +19,11 @@ struct MatFwdParams {
     T* hi;
     int64_t batch, n, n_in, x_stride, lo_stride, hi_stride;
     int L, shift, odd_mode;
-    int nb_top, nb_bot, w_top, w_bot;
-    const T* lo_top;
-    const T* lo_bot;
-    const T* hi_top;
-    const T* hi_bot;
+    int nb_top, nb_bot, w_left, w_right;
+    const T* lo_left;   // [nb_top + nb_bot, w_left]
+    const T* lo_right;  // [nb_top + nb_bot, w_right]
+    const T* hi_left;
+    const T* hi_right;
     Taps<T> taps;  // un-flipped dec_lo / dec_hi
 };
 
@@ -50,23 +50,23 @@ __global__ void __launch_bounds__(256) mat_fwd_kernel(const __grid_constant__ Ma
         const int64_t b = idx / half;
         const T* __restrict__ xb = p.x + b * p.x_stride;
         T alo = T(0), ahi = T(0);
-        if (i < p.nb_top) {
-            const T* __restrict__ rl = p.lo_top + i * p.w_top;
-            const T* __restrict__ rh = p.hi_top + i * p.w_top;
-            for (int c = 0; c < p.w_top; ++c) {
+        if (i < p.nb_top || i >= half - p.nb_bot) {
+            // orthogonalised boundary row: dense dot over the two corner windows
+            const int64_t r = i < p.nb_top ? i : p.nb_top + (i - (half - p.nb_bot));
+            const T* __restrict__ ll = p.lo_left + r * p.w_left;
+            const T* __restrict__ hl = p.hi_left + r * p.w_left;
+            for (int c = 0; c < p.w_left; ++c) {
                 const T v = mat_sample(xb, (int64_t)c, p.n_in, p.odd_mode);
-                alo = fma(__ldg(rl + c), v, alo);
-                ahi = fma(__ldg(rh + c), v, ahi);
+                alo = fma(__ldg(ll + c), v, alo);
+                ahi = fma(__ldg(hl + c), v, ahi);
             }
-        } else if (i >= half - p.nb_bot) {
-            const int64_t r = i - (half - p.nb_bot);
-            const T* __restrict__ rl = p.lo_bot + r * p.w_bot;
-            const T* __restrict__ rh = p.hi_bot + r * p.w_bot;
-            const int64_t c0 = p.n - p.w_bot;
-            for (int c = 0; c < p.w_bot; ++c) {
+            const T* __restrict__ lr = p.lo_right + r * p.w_right;
+            const T* __restrict__ hr = p.hi_right + r * p.w_right;
+            const int64_t c0 = p.n - p.w_right;
+            for (int c = 0; c < p.w_right; ++c) {
                 const T v = mat_sample(xb, c0 + c, p.n_in, p.odd_mode);
-                alo = fma(__ldg(rl + c), v, alo);
-                ahi = fma(__ldg(rh + c), v, ahi);
+                alo = fma(__ldg(lr + c), v, alo);
+                ahi = fma(__ldg(hr + c), v, ahi);
             }
         } else {
             const int64_t top = 2 * i + p.shift;  // column hit by tap 0
@@ -90,11 +90,11 @@ struct MatInvParams {
     T* y;         // [batch, keep]
     int64_t batch, n, keep, lo_stride, hi_stride, y_stride;
     int L, shift;
-    int nb_top, nb_bot, w_top, w_bot;
-    const T* lo_top;
-    const T* lo_bot;
-    const T* hi_top;
-    const T* hi_bot;
+    int nb_top, nb_bot, w_left, w_right;
+    const T* lo_left;
+    const T* lo_right;
+    const T* hi_left;
+    const T* hi_right;
     Taps<T> taps;  // FLIPPED rec_lo / rec_hi (rows of S^T, reference matmul_transform.py:110-116)
 };
 
@@ -121,19 +121,21 @@ __global__ void __launch_bounds__(256) mat_inv_kernel(const __grid_constant__ Ma
             acc = fma(p.taps.lo[m], __ldg(lb + i), acc);
             acc = fma(p.taps.hi[m], __ldg(hb + i), acc);
         }
-        if (t < p.w_top) {
-            for (int r = 0; r < p.nb_top; ++r) {
-                acc = fma(__ldg(p.lo_top + r * p.w_top + t), __ldg(lb + r), acc);
-                acc = fma(__ldg(p.hi_top + r * p.w_top + t), __ldg(hb + r), acc);
+        const int nb = p.nb_top + p.nb_bot;
+        if (t < p.w_left) {
+            for (int r = 0; r < nb; ++r) {
+                const int64_t i = r < p.nb_top ? r : half - p.nb_bot + (r - p.nb_top);
+                acc = fma(__ldg(p.lo_left + r * p.w_left + t), __ldg(lb + i), acc);
+                acc = fma(__ldg(p.hi_left + r * p.w_left + t), __ldg(hb + i), acc);
             }
         }
-        const int64_t c0 = p.n - p.w_bot;
+        const int64_t c0 = p.n - p.w_right;
         if (t >= c0) {
             const int64_t c = t - c0;
-            for (int r = 0; r < p.nb_bot; ++r) {
-                const int64_t i = half - p.nb_bot + r;
-                acc = fma(__ldg(p.lo_bot + r * p.w_bot + c), __ldg(lb + i), acc);
-                acc = fma(__ldg(p.hi_bot + r * p.w_bot + c), __ldg(hb + i), acc);
+            for (int r = 0; r < nb; ++r) {
+                const int64_t i = r < p.nb_top ? r : half - p.nb_bot + (r - p.nb_top);
+                acc = fma(__ldg(p.lo_right + r * p.w_right + c), __ldg(lb + i), acc);
+                acc = fma(__ldg(p.hi_right + r * p.w_right + c), __ldg(hb + i), acc);
             }
         }
         p.y[b * p.y_stride + t] = acc;

@@ -14,6 +14,9 @@
 #include "common.cuh"
 #include "generic_axis.cuh"
 #include "matrix_generic.cuh"
+#if !defined(WTB_NO_FUSED) && !__has_include("fused2d.cuh")
+#define WTB_NO_FUSED 1
+#endif
 #ifndef WTB_NO_FUSED
 #include "fused2d.cuh"
 #endif
@@ -426,11 +429,12 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
         p.lo = last ? (T*)lo_out : ping[l & 1];
         p.lo_stride = last ? lo_stride : n[l] / 2;
         p.L = L; p.shift = L / 2 + (L % 2); p.odd_mode = odd_mode;
-        p.nb_top = nbt[l]; p.nb_bot = nbb[l]; p.w_top = wt[l]; p.w_bot = wb[l];
-        p.lo_top = blk; blk += (int64_t)nbt[l] * wt[l];
-        p.lo_bot = blk; blk += (int64_t)nbb[l] * wb[l];
-        p.hi_top = blk; blk += (int64_t)nbt[l] * wt[l];
-        p.hi_bot = blk; blk += (int64_t)nbb[l] * wb[l];
+        p.nb_top = nbt[l]; p.nb_bot = nbb[l]; p.w_left = wt[l]; p.w_right = wb[l];
+        const int64_t nb = (int64_t)nbt[l] + nbb[l];
+        p.lo_left = blk; blk += nb * wt[l];
+        p.lo_right = blk; blk += nb * wb[l];
+        p.hi_left = blk; blk += nb * wt[l];
+        p.hi_right = blk; blk += nb * wb[l];
         p.taps = taps;
         const int64_t total = batch * (n[l] / 2);
         if (total > 0) {
@@ -460,7 +464,7 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
     int64_t o = 0;
     for (int l = 0; l < levels; ++l) {
         off[l] = o;
-        o += 2 * ((int64_t)nbt[l] * wt[l] + (int64_t)nbb[l] * wb[l]);
+        o += 2 * ((int64_t)nbt[l] + nbb[l]) * ((int64_t)wt[l] + wb[l]);
     }
     const T* src = (const T*)lo_in;
     int64_t src_stride = lo_stride;
@@ -476,12 +480,13 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
         p.y = last ? (T*)y : ping[l & 1];
         p.y_stride = last ? ys : p.keep;
         p.L = L; p.shift = L / 2 + (L % 2);
-        p.nb_top = nbt[l]; p.nb_bot = nbb[l]; p.w_top = wt[l]; p.w_bot = wb[l];
+        p.nb_top = nbt[l]; p.nb_bot = nbb[l]; p.w_left = wt[l]; p.w_right = wb[l];
         const T* blk = (const T*)blocks + off[l];
-        p.lo_top = blk; blk += (int64_t)nbt[l] * wt[l];
-        p.lo_bot = blk; blk += (int64_t)nbb[l] * wb[l];
-        p.hi_top = blk; blk += (int64_t)nbt[l] * wt[l];
-        p.hi_bot = blk;
+        const int64_t nb = (int64_t)nbt[l] + nbb[l];
+        p.lo_left = blk; blk += nb * wt[l];
+        p.lo_right = blk; blk += nb * wb[l];
+        p.hi_left = blk; blk += nb * wt[l];
+        p.hi_right = blk;
         p.taps = taps;
         const int64_t total = batch * p.keep;
         if (total > 0) {
@@ -564,45 +569,45 @@ int wt_dwt_inv(int ndim, int dtype, int levels, int filt_len, const double* rec_
 
 int wt_matrix_fwd(int dtype, int levels, int filt_len, const double* dec_lo, const double* dec_hi,
                   const int64_t* n, const int32_t* padded, int odd_mode, const int32_t* nb_top,
-                  const int32_t* nb_bot, const int32_t* w_top, const int32_t* w_bot, const void* blocks,
+                  const int32_t* nb_bot, const int32_t* w_left, const int32_t* w_right, const void* blocks,
                   const void* x, int64_t batch, int64_t x_stride, void* const* hi_out, const int64_t* hi_stride,
                   void* lo_out, int64_t lo_stride, void* scratch, size_t scratch_bytes, void* stream) {
     if (dtype != WT_F32 && dtype != WT_F64) return fail(WT_EINVAL, "dtype must be WT_F32 or WT_F64");
     if (levels < 1) return fail(WT_EINVAL, "levels must be >= 1");
     if (filt_len < 2 || filt_len > WT_MAX_FILT_LEN) return fail(WT_EUNSUPPORTED, "filter length %d", filt_len);
     if (odd_mode < WT_MODE_ZERO || odd_mode > WT_MODE_SYMMETRIC) return fail(WT_EINVAL, "unknown padding mode %d", odd_mode);
-    if (!dec_lo || !dec_hi || !n || !padded || !nb_top || !nb_bot || !w_top || !w_bot || !hi_out || !hi_stride)
+    if (!dec_lo || !dec_hi || !n || !padded || !nb_top || !nb_bot || !w_left || !w_right || !hi_out || !hi_stride)
         return fail(WT_EINVAL, "NULL argument");
     if (batch == 0) return 0;
     if (!x || !lo_out) return fail(WT_EINVAL, "NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == WT_F32)
-        return matrix_fwd_t<float>(levels, filt_len, dec_lo, dec_hi, n, padded, odd_mode, nb_top, nb_bot, w_top,
-                                   w_bot, blocks, x, batch, x_stride, hi_out, hi_stride, lo_out, lo_stride,
+        return matrix_fwd_t<float>(levels, filt_len, dec_lo, dec_hi, n, padded, odd_mode, nb_top, nb_bot, w_left,
+                                   w_right, blocks, x, batch, x_stride, hi_out, hi_stride, lo_out, lo_stride,
                                    scratch, scratch_bytes, st);
-    return matrix_fwd_t<double>(levels, filt_len, dec_lo, dec_hi, n, padded, odd_mode, nb_top, nb_bot, w_top,
-                                w_bot, blocks, x, batch, x_stride, hi_out, hi_stride, lo_out, lo_stride, scratch,
+    return matrix_fwd_t<double>(levels, filt_len, dec_lo, dec_hi, n, padded, odd_mode, nb_top, nb_bot, w_left,
+                                w_right, blocks, x, batch, x_stride, hi_out, hi_stride, lo_out, lo_stride, scratch,
                                 scratch_bytes, st);
 }
 
 int wt_matrix_inv(int dtype, int levels, int filt_len, const double* rec_lo, const double* rec_hi,
                   const int64_t* n, const int64_t* next_len, const int32_t* nb_top, const int32_t* nb_bot,
-                  const int32_t* w_top, const int32_t* w_bot, const void* blocks, const void* lo_in,
+                  const int32_t* w_left, const int32_t* w_right, const void* blocks, const void* lo_in,
                   int64_t lo_stride, const void* const* hi_in, const int64_t* hi_stride, int64_t batch, void* y,
                   int64_t y_stride, void* scratch, size_t scratch_bytes, void* stream) {
     if (dtype != WT_F32 && dtype != WT_F64) return fail(WT_EINVAL, "dtype must be WT_F32 or WT_F64");
     if (levels < 1) return fail(WT_EINVAL, "levels must be >= 1");
     if (filt_len < 2 || filt_len > WT_MAX_FILT_LEN) return fail(WT_EUNSUPPORTED, "filter length %d", filt_len);
-    if (!rec_lo || !rec_hi || !n || !next_len || !nb_top || !nb_bot || !w_top || !w_bot || !hi_in || !hi_stride)
+    if (!rec_lo || !rec_hi || !n || !next_len || !nb_top || !nb_bot || !w_left || !w_right || !hi_in || !hi_stride)
         return fail(WT_EINVAL, "NULL argument");
     if (batch == 0) return 0;
     if (!lo_in || !y) return fail(WT_EINVAL, "NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == WT_F32)
-        return matrix_inv_t<float>(levels, filt_len, rec_lo, rec_hi, n, next_len, nb_top, nb_bot, w_top, w_bot,
+        return matrix_inv_t<float>(levels, filt_len, rec_lo, rec_hi, n, next_len, nb_top, nb_bot, w_left, w_right,
                                    blocks, lo_in, lo_stride, hi_in, hi_stride, batch, y, y_stride, scratch,
                                    scratch_bytes, st);
-    return matrix_inv_t<double>(levels, filt_len, rec_lo, rec_hi, n, next_len, nb_top, nb_bot, w_top, w_bot,
+    return matrix_inv_t<double>(levels, filt_len, rec_lo, rec_hi, n, next_len, nb_top, nb_bot, w_left, w_right,
                                 blocks, lo_in, lo_stride, hi_in, hi_stride, batch, y, y_stride, scratch,
                                 scratch_bytes, st);
 }

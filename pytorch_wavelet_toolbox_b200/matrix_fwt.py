@@ -115,13 +115,19 @@ def orthogonalize_rows(sel: torch.Tensor, method: str) -> torch.Tensor:
 
 
 class _LevelBlocks:
-    """Boundary rows of one level operator, ready for the kernels."""
+    """Boundary rows of one level operator, ready for the kernels.
 
-    __slots__ = ("n", "nb_top", "nb_bot", "w_top", "w_bot", "lo_top", "lo_bot", "hi_top", "hi_bot")
+    ``nb_top + nb_bot`` rows per half (top rows first).  Every row is stored as a left window (first
+    ``w_left`` columns) and a right window (last ``w_right`` columns): the orthogonalisation leaves
+    round-off sized entries of a top row in the right corner and vice versa, and they are kept
+    because the reference keeps them (``q.T.to_sparse()``, sparse_math.py:285).
+    """
+
+    __slots__ = ("n", "nb_top", "nb_bot", "w_left", "w_right", "lo_left", "lo_right", "hi_left", "hi_right")
 
     def flat(self) -> torch.Tensor:
-        return torch.cat([self.lo_top.reshape(-1), self.lo_bot.reshape(-1), self.hi_top.reshape(-1),
-                          self.hi_bot.reshape(-1)])
+        return torch.cat([self.lo_left.reshape(-1), self.lo_right.reshape(-1), self.hi_left.reshape(-1),
+                          self.hi_right.reshape(-1)])
 
 
 @functools.lru_cache(maxsize=256)
@@ -137,33 +143,24 @@ def _level_blocks_cached(lo_key: bytes, hi_key: bytes, dtype_name: str, n: int, 
     blk.nb_top, blk.nb_bot = len(top), len(bot)
     if not ids:
         z = torch.zeros((0, 0), dtype=dtype)
-        blk.w_top = blk.w_bot = 0
-        blk.lo_top = blk.lo_bot = blk.hi_top = blk.hi_bot = z
+        blk.w_left = blk.w_right = 0
+        blk.lo_left = blk.lo_right = blk.hi_left = blk.hi_right = z
         return blk
     # one slab, rows in the reference's order: boundary rows of the lo half (ascending), then of
     # the hi half (reference matmul_transform.py:121-136: unique row indices of cat([A_lo, A_hi]))
     sel = torch.cat([_raw_rows(lo, n, ids), _raw_rows(hi, n, ids)], 0)
     q = orthogonalize_rows(sel, method)
     nb = len(ids)
-    q_lo, q_hi = q[:nb], q[nb:]
-    nt = len(top)
-    tops = torch.cat([q_lo[:nt], q_hi[:nt]], 0)
-    bots = torch.cat([q_lo[nt:], q_hi[nt:]], 0)
-
-    def _extent(rows: torch.Tensor, from_left: bool) -> int:
-        if rows.shape[0] == 0:
-            return 0
-        nz = (rows != 0).any(0).nonzero().reshape(-1)
-        if nz.numel() == 0:
-            return 0
-        return int(nz.max()) + 1 if from_left else n - int(nz.min())
-
-    blk.w_top = _extent(tops, True)
-    blk.w_bot = _extent(bots, False)
-    blk.lo_top = q_lo[:nt, : blk.w_top].contiguous()
-    blk.hi_top = q_hi[:nt, : blk.w_top].contiguous()
-    blk.lo_bot = q_lo[nt:, n - blk.w_bot:].contiguous()
-    blk.hi_bot = q_hi[nt:, n - blk.w_bot:].contiguous()
+    nz = (q != 0).any(0).nonzero().reshape(-1)
+    half = n // 2
+    left = nz[nz < half]
+    right = nz[nz >= half]
+    blk.w_left = int(left.max()) + 1 if left.numel() else 0
+    blk.w_right = n - int(right.min()) if right.numel() else 0
+    blk.lo_left = q[:nb, : blk.w_left].contiguous()
+    blk.hi_left = q[nb:, : blk.w_left].contiguous()
+    blk.lo_right = q[:nb, n - blk.w_right:].contiguous()
+    blk.hi_right = q[nb:, n - blk.w_right:].contiguous()
     return blk
 
 
@@ -202,10 +199,13 @@ def _level_operator_sparse(lo_taps: np.ndarray, hi_taps: np.ndarray, dtype: torc
             keep = block != 0
             idx.append(torch.stack([rr[keep] + row0, cc[keep] + col0]))
             vals.append(block[keep])
-        add(blk.lo_top, 0, 0)
-        add(blk.lo_bot, half - blk.nb_bot, n - blk.w_bot)
-        add(blk.hi_top, half, 0)
-        add(blk.hi_bot, n - blk.nb_bot, n - blk.w_bot)
+        nt = blk.nb_top
+        for band, (bl, br) in enumerate(((blk.lo_left, blk.lo_right), (blk.hi_left, blk.hi_right))):
+            base = band * half
+            add(bl[:nt], base, 0)
+            add(br[:nt], base, n - blk.w_right)
+            add(bl[nt:], base + half - blk.nb_bot, 0)
+            add(br[nt:], base + half - blk.nb_bot, n - blk.w_right)
     mat = torch.sparse_coo_tensor(torch.cat(idx, 1), torch.cat(vals), size=(n, n), dtype=dtype)
     return mat.coalesce().to(device)
 
@@ -412,8 +412,8 @@ class MatrixWavedec:
             pd_arr, pd_p = N.i32_array(padded)
             nbt_arr, nbt_p = N.i32_array([b.nb_top for b in blocks])
             nbb_arr, nbb_p = N.i32_array([b.nb_bot for b in blocks])
-            wt_arr, wt_p = N.i32_array([b.w_top for b in blocks])
-            wb_arr, wb_p = N.i32_array([b.w_bot for b in blocks])
+            wt_arr, wt_p = N.i32_array([b.w_left for b in blocks])
+            wb_arr, wb_p = N.i32_array([b.w_right for b in blocks])
             lo_arr, lo_p = N.f64_array(lo_t)
             hi_arr, hi_p = N.f64_array(hi_t)
             scratch_elems = 2 * batch * (sizes[0] // 2) if nl > 1 else 0
@@ -563,8 +563,8 @@ class MatrixWaverec:
             k_arr, k_p = N.i64_array(keep)
             nbt_arr, nbt_p = N.i32_array([b.nb_top for b in blocks])
             nbb_arr, nbb_p = N.i32_array([b.nb_bot for b in blocks])
-            wt_arr, wt_p = N.i32_array([b.w_top for b in blocks])
-            wb_arr, wb_p = N.i32_array([b.w_bot for b in blocks])
+            wt_arr, wt_p = N.i32_array([b.w_left for b in blocks])
+            wb_arr, wb_p = N.i32_array([b.w_right for b in blocks])
             lo_arr, lo_p = N.f64_array(taps_in_dtype(rec_lo, dt))
             hi_arr, hi_p = N.f64_array(taps_in_dtype(rec_hi, dt))
             scratch_elems = 2 * batch * sizes[0] if nl > 1 else 0

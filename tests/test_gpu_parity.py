@@ -1,0 +1,333 @@
+"""Parity of the CUDA path (through the public API -> ctypes -> C ABI -> kernels) with the oracle.
+
+Tolerances (stated): |delta| <= 1e-5 * max|c| in float32 and 1e-11 * max|c| in
+float64, where c is the oracle's coefficient tensor; round-trip errors are reported against the
+input's max.  The oracle (oracle/ptwt_port.py) runs the reference's own torch-CPU operator sequence.
+"""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+import torch
+
+import pytorch_wavelet_toolbox_b200 as wt
+from conftest import TOL, assert_close_rel, flatten_coeffs
+from oracle import ptwt_port as P
+
+pytestmark = pytest.mark.gpu
+
+MODES = ("zero", "constant", "reflect", "periodic", "symmetric")
+DEV = "cuda"
+
+
+def _cmp_tree(got, want, what):
+    fg, fw = flatten_coeffs(got), flatten_coeffs(want)
+    assert len(fg) == len(fw), what
+    assert type(got) is type(want), what
+    scale = max(float(t.abs().max()) for t in fw if t.numel())
+    for j, (a, b) in enumerate(zip(fg, fw)):
+        assert a.is_cuda
+        assert_close_rel(a, b, scale=scale, what=f"{what} tensor {j}")
+
+
+def _run(case, x, mod):
+    fam, wav, mode, level, axes = case["family"], case["wavelet"], case["mode"], case["level"], case["axes"]
+    if isinstance(axes, list):
+        axes = tuple(axes)
+    if fam == "wavedec":
+        kw = {} if axes is None else {"axis": axes}
+        c = mod.wavedec(x, wav, mode=mode, level=level, **kw)
+        return c, mod.waverec(c, wav, **kw)
+    if fam == "wavedec2":
+        kw = {} if axes is None else {"axes": axes}
+        c = mod.wavedec2(x, wav, mode=mode, level=level, **kw)
+        return c, mod.waverec2(c, wav, **kw)
+    if fam == "wavedec3":
+        kw = {} if axes is None else {"axes": axes}
+        c = mod.wavedec3(x, wav, mode=mode, level=level, **kw)
+        return c, mod.waverec3(c, wav, **kw)
+    meth = "gramschmidt" if fam == "matrix_gs" else "qr"
+    c = mod.MatrixWavedec(wav, level, orthogonalization=meth, odd_coeff_padding_mode=mode)(x)
+    return c, mod.MatrixWaverec(wav, orthogonalization=meth)(c)
+
+
+def test_native_library_is_the_one_running():
+    from pytorch_wavelet_toolbox_b200 import _native
+
+    _native.launch_count_reset()
+    wt.wavedec(torch.randn(4, 64, device=DEV), "db2", level=2)
+    assert _native.launch_count() >= 1
+
+
+@pytest.mark.parametrize("on_host", [False, True])
+def test_golden_vectors_from_the_reference(golden, on_host):
+    """Every committed fixture the unmodified reference produced, through the CUDA path; CUDA tensors
+    and CPU tensors (staged through the device) give the same numbers."""
+    manifest, arrays = golden
+    for case in manifest["cases"]:
+        i = case["id"]
+        x = torch.from_numpy(arrays[f"c{i}_x"])
+        xin = x if on_host else x.to(DEV)
+        c, rec = _run(case, xin, wt)
+        flat = flatten_coeffs(c)
+        assert len(flat) == case["n_out"]
+        want = [torch.from_numpy(arrays[f"c{i}_o{j}"]) for j in range(case["n_out"])]
+        scale = max(float(t.abs().max()) for t in want)
+        for j, t in enumerate(flat):
+            assert t.device.type == ("cpu" if on_host else "cuda")
+            assert_close_rel(t, want[j], scale=scale, what=f"case {i} ({case['family']} {case['wavelet']}) out {j}")
+        wrec = torch.from_numpy(arrays[f"c{i}_rec"])
+        assert_close_rel(rec, wrec, scale=10 * float(wrec.abs().max()), what=f"case {i} reconstruction")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("mode", MODES)
+def test_wavedec_1d_sweep(dtype, mode):
+    g = torch.Generator().manual_seed(11)
+    for wav in ("haar", "db2", "db3", "db4", "db5", "sym5", "db8"):
+        for n in (64, 65, 31, 257):
+            for level in (1, 2, None):
+                x = torch.randn(3, n, generator=g, dtype=torch.float64).to(dtype)
+                try:
+                    want = P.wavedec(x, wav, mode=mode, level=level)
+                except RuntimeError:
+                    with pytest.raises(RuntimeError):
+                        wt.wavedec(x.to(DEV), wav, mode=mode, level=level)
+                    continue
+                got = wt.wavedec(x.to(DEV), wav, mode=mode, level=level)
+                _cmp_tree(got, want, f"wavedec {wav} {mode} n={n} level={level}")
+                rec = wt.waverec(got, wav)
+                assert_close_rel(rec, P.waverec(want, wav), scale=10 * float(x.abs().max()), what="waverec")
+                assert_close_rel(rec[..., :n], x, scale=10 * float(x.abs().max()), what="round trip")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("mode", MODES)
+def test_wavedec2_sweep(dtype, mode):
+    g = torch.Generator().manual_seed(12)
+    for wav in ("haar", "db2", "db4", "sym4", "db8"):
+        for shape in ((64, 64), (33, 40), (31, 31), (65, 128), (130, 47)):
+            for level in (1, 2, None):
+                x = torch.randn((2,) + shape, generator=g, dtype=torch.float64).to(dtype)
+                try:
+                    want = P.wavedec2(x, wav, mode=mode, level=level)
+                except RuntimeError:
+                    with pytest.raises(RuntimeError):
+                        wt.wavedec2(x.to(DEV), wav, mode=mode, level=level)
+                    continue
+                got = wt.wavedec2(x.to(DEV), wav, mode=mode, level=level)
+                _cmp_tree(got, want, f"wavedec2 {wav} {mode} {shape} level={level}")
+                if len(got) > 1:
+                    assert isinstance(got[1], tuple) and got[1]._fields == ("horizontal", "vertical", "diagonal")
+                rec = wt.waverec2(got, wav)
+                assert_close_rel(rec, P.waverec2(want, wav), scale=10 * float(x.abs().max()), what="waverec2")
+                assert_close_rel(rec[..., : shape[0], : shape[1]], x, scale=10 * float(x.abs().max()), what="round trip")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+@pytest.mark.parametrize("mode", MODES)
+def test_wavedec3_sweep(dtype, mode):
+    g = torch.Generator().manual_seed(13)
+    for wav in ("haar", "db2", "sym4"):
+        for shape in ((16, 16, 16), (17, 18, 19), (31, 32, 33), (8, 40, 21)):
+            for level in (1, 2, None):
+                x = torch.randn((2,) + shape, generator=g, dtype=torch.float64).to(dtype)
+                try:
+                    want = P.wavedec3(x, wav, mode=mode, level=level)
+                except RuntimeError:
+                    with pytest.raises(RuntimeError):
+                        wt.wavedec3(x.to(DEV), wav, mode=mode, level=level)
+                    continue
+                got = wt.wavedec3(x.to(DEV), wav, mode=mode, level=level)
+                _cmp_tree(got, want, f"wavedec3 {wav} {mode} {shape} level={level}")
+                rec = wt.waverec3(got, wav)
+                assert_close_rel(rec, P.waverec3(want, wav), scale=10 * float(x.abs().max()), what="waverec3")
+                sl = tuple(slice(0, s) for s in shape)
+                assert_close_rel(rec[(Ellipsis,) + sl], x, scale=10 * float(x.abs().max()), what="round trip")
+
+
+def test_axes_batch_folding_and_missing_batch_dim():
+    """tests/test_convolution_fwt.py:270-388 and tests/test_convolution_fwt_3.py:100-164 of the reference."""
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(2, 20, 22, 24, 26, generator=g, dtype=torch.float64)
+    xd = x.to(DEV)
+    _cmp_tree(wt.wavedec(xd, "db2", level=2, axis=2), P.wavedec(x, "db2", level=2, axis=2), "axis=2")
+    _cmp_tree(wt.wavedec2(xd, "db2", level=2, axes=(1, 3)), P.wavedec2(x, "db2", level=2, axes=(1, 3)), "axes=(1,3)")
+    _cmp_tree(wt.wavedec2(xd, "db3", level=1, axes=(-1, 0)), P.wavedec2(x, "db3", level=1, axes=(-1, 0)), "axes=(-1,0)")
+    _cmp_tree(wt.wavedec3(xd, "db2", level=1, axes=(4, 1, 2)), P.wavedec3(x, "db2", level=1, axes=(4, 1, 2)), "axes3")
+    c = wt.wavedec2(xd, "db2", level=2, axes=(1, 3))
+    assert_close_rel(wt.waverec2(c, "db2", axes=(1, 3)), x, scale=10.0, what="axes round trip")
+    c = wt.wavedec3(xd, "db2", level=1, axes=(4, 1, 2))
+    assert_close_rel(wt.waverec3(c, "db2", axes=(4, 1, 2)), x, scale=10.0, what="axes3 round trip")
+    c = wt.wavedec(xd, "db2", level=2, axis=2)
+    assert_close_rel(wt.waverec(c, "db2", axis=2), x, scale=10.0, what="axis round trip")
+    # no batch dimension
+    v = torch.randn(50, generator=g, dtype=torch.float64)
+    _cmp_tree(wt.wavedec(v.to(DEV), "db3", level=2), P.wavedec(v, "db3", level=2), "no batch 1d")
+    m = torch.randn(33, 35, generator=g)
+    _cmp_tree(wt.wavedec2(m.to(DEV), "db2", level=2), P.wavedec2(m, "db2", level=2), "no batch 2d")
+    vol = torch.randn(12, 13, 14, generator=g)
+    _cmp_tree(wt.wavedec3(vol.to(DEV), "haar", level=1), P.wavedec3(vol, "haar", level=1), "no batch 3d")
+    # non-contiguous input
+    xt = torch.randn(40, 6, generator=g, dtype=torch.float64)
+    _cmp_tree(wt.wavedec(xt.to(DEV).T, "db2", level=2), P.wavedec(xt.T, "db2", level=2), "transposed input")
+
+
+def test_waverec_accepts_foreign_layouts():
+    """Coefficients that did not come from this package (contiguous tensors, the oracle's channel-slice
+    views) go through the gather path; ours go through zero-copy. Both must agree."""
+    g = torch.Generator().manual_seed(15)
+    x = torch.randn(3, 45, 52, generator=g, dtype=torch.float64)
+    want = P.wavedec2(x, "db3", level=2)
+    foreign = tuple([want[0].to(DEV)] + [wt.WaveletDetailTuple2d(*[t.to(DEV).contiguous() for t in lv]) for lv in want[1:]])
+    rec_f = wt.waverec2(foreign, "db3")
+    rec_o = wt.waverec2(wt.wavedec2(x.to(DEV), "db3", level=2), "db3")
+    ref = P.waverec2(want, "db3")
+    assert_close_rel(rec_f, ref, scale=10.0, what="foreign layout")
+    assert_close_rel(rec_o, ref, scale=10.0, what="own layout")
+    # plain tuples instead of the named tuple, lists for 1-D
+    c1 = P.wavedec(x, "db2", level=3)
+    assert_close_rel(wt.waverec(tuple(t.to(DEV) for t in c1), "db2"), P.waverec(c1, "db2"), scale=10.0, what="tuple in")
+
+
+def test_custom_filter_bank_objects_and_tensor_tuples():
+    g = torch.Generator().manual_seed(16)
+
+    class MyHaar:
+        name = "unscaled Haar"
+        filter_bank = ([0.5, 0.5], [-0.5, 0.5], [0.5, 0.5], [0.5, -0.5])
+        dec_lo, dec_hi, rec_lo, rec_hi = filter_bank
+        dec_len = rec_len = 2
+
+        def __len__(self):
+            return 2
+
+    x = torch.tensor([56.0, 40.0, 8.0, 24.0, 48.0, 48.0, 40.0, 16.0], device=DEV)
+    c = wt.wavedec(x, MyHaar(), level=3)  # Ripples in Mathematics p.7 (reference test_convolution_fwt.py:98-118)
+    for got, w in zip(c, ([35.0], [-3.0], [16.0, 10.0], [8.0, -8.0, 0.0, 12.0])):
+        assert torch.equal(got.reshape(-1).cpu(), torch.tensor(w))
+    from pytorch_wavelet_toolbox_b200._wavelets import as_wavelet
+
+    w = as_wavelet("db3")
+    tt = wt.WaveletTensorTuple.from_wavelet(w, torch.float64)
+    xx = torch.randn(2, 40, generator=g, dtype=torch.float64)
+    _cmp_tree(wt.wavedec(xx.to(DEV), tt, level=2), P.wavedec(xx, "db3", level=2), "tensor tuple wavelet")
+
+
+def test_readme_example_config0():
+    """BASELINE.json configs[0]: haar, zero, level 2, len 16, float32, CPU tensor in -> CPU tensors out."""
+    x = torch.tensor([0, 1, 2, 3, 4, 5, 6, 7, 7, 6, 5, 4, 3, 2, 1, 0], dtype=torch.float32)
+    c = wt.wavedec(x, "haar", mode="zero", level=2)
+    assert all(t.device.type == "cpu" for t in c)
+    s = 0.5 ** 0.5
+    assert torch.allclose(c[0], torch.tensor([3.0, 11.0, 11.0, 3.0]), atol=1e-6)
+    assert torch.allclose(c[1], torch.tensor([-2.0, -2.0, 2.0, 2.0]), atol=1e-6)
+    assert torch.allclose(c[2], torch.tensor([-s] * 4 + [s] * 4), atol=1e-6)
+    assert (wt.waverec(c, "haar") - x).abs().max() < 1e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_matrix_fwt_sweep(dtype):
+    g = torch.Generator().manual_seed(17)
+    for wav in ("haar", "db2", "db3", "db4", "db6", "sym5", "db8"):
+        for n in (32, 33, 64, 100, 127, 256):
+            for level in (1, 2, 3, None):
+                for meth in ("qr", "gramschmidt"):
+                    for odd_mode in ("zero", "reflect"):
+                        x = torch.randn(4, n, generator=g, dtype=torch.float64).to(dtype)
+                        ref_fw = P.MatrixWavedec(wav, level, orthogonalization=meth, odd_coeff_padding_mode=odd_mode)
+                        want = ref_fw(x)
+                        fw = wt.MatrixWavedec(wav, level, orthogonalization=meth, odd_coeff_padding_mode=odd_mode)
+                        got = fw(x.to(DEV))
+                        assert len(got) == len(want)
+                        scale = max(float(t.abs().max()) for t in want)
+                        tag = f"matrix {wav} n={n} level={level} {meth} {odd_mode}"
+                        for a, b in zip(got, want):
+                            assert_close_rel(a, b.contiguous(), scale=scale, what=tag)
+                        if len(want) == 1:
+                            continue
+                        rec = wt.MatrixWaverec(wav, orthogonalization=meth)(got)
+                        wrec = P.MatrixWaverec(wav, orthogonalization=meth)(want)
+                        assert_close_rel(rec, wrec.contiguous(), scale=10 * float(x.abs().max()), what=tag + " inverse")
+
+
+def test_matrix_round_trip_and_orthogonality_config4_shape():
+    """BASELINE.json configs[3] geometry at a reduced batch: db6, len 65536, float64, level None -> 12."""
+    g = torch.Generator().manual_seed(18)
+    x = torch.randn(8, 65536, generator=g, dtype=torch.float64)
+    fw = wt.MatrixWavedec("db6")
+    c = fw(x.to(DEV))
+    assert fw.level == 12 and [t.shape[-1] for t in c] == [16] + [16 * 2 ** k for k in range(12)]
+    want = P.MatrixWavedec("db6")(x)
+    scale = max(float(t.abs().max()) for t in want)
+    for a, b in zip(c, want):
+        assert_close_rel(a, b.contiguous(), scale=scale, what="cfg4 coefficients")
+    rec = wt.MatrixWaverec("db6")(c)
+    assert float((rec.cpu() - x).abs().max()) < 1e-11      # reference: 1.8e-14
+    # orthogonal transform: energy is preserved
+    e_in = float((x ** 2).sum())
+    e_out = sum(float((t.double() ** 2).sum()) for t in c)
+    assert abs(e_in - e_out) / e_in < 1e-12
+    # operator property agrees with applying the transform
+    small = wt.MatrixWavedec("db4", 3)
+    xs = torch.randn(5, 64, generator=g, dtype=torch.float64)
+    cs = small(xs.to(DEV))
+    op = small.sparse_fwt_operator.to_dense()
+    assert_close_rel(torch.cat([t.cpu() for t in cs], -1), (op @ xs.T).T.contiguous(), scale=10.0, what="operator")
+    inv = wt.MatrixWaverec("db4")
+    inv(cs)
+    eye = inv.sparse_ifwt_operator.to_dense() @ op
+    assert (eye - torch.eye(64, dtype=torch.float64)).abs().max() < 1e-8
+
+
+def test_full_size_properties_config2():
+    """BASELINE.json configs[1] geometry (4096x4096 float32, db4, level 4, reflect) on 2 images:
+    extents, parity against the oracle on one image, round trip, linearity."""
+    g = torch.Generator(device=DEV).manual_seed(1234)
+    x = torch.randn(2, 4096, 4096, generator=g, device=DEV, dtype=torch.float32)
+    c = wt.wavedec2(x, "db4", level=4)
+    assert c[0].shape == (2, 262, 262)
+    assert [lv.horizontal.shape[-1] for lv in c[1:]] == [262, 518, 1029, 2051]
+    want = P.wavedec2(x[:1].cpu(), "db4", level=4)
+    scale = max(float(t.abs().max()) for t in flatten_coeffs(want))
+    for a, b in zip(flatten_coeffs(c), flatten_coeffs(want)):
+        assert_close_rel(a[:1], b, scale=scale, what="cfg2 coefficients")
+    rec = wt.waverec2(c, "db4")
+    err = float((rec - x).abs().max())
+    assert err < 2e-5, err          # reference itself: 1.9e-6
+    y = torch.randn(2, 4096, 4096, generator=g, device=DEV, dtype=torch.float32)
+    cy = wt.wavedec2(y, "db4", level=4)
+    cz = wt.wavedec2(2.0 * x - y, "db4", level=4)
+    for a, b, z in zip(flatten_coeffs(c), flatten_coeffs(cy), flatten_coeffs(cz)):
+        assert float((2.0 * a - b - z).abs().max()) < 2e-4
+
+
+def test_full_size_properties_config3():
+    """BASELINE.json configs[2] geometry (256^3 float32, sym4, level 3, zero) on 1 volume."""
+    g = torch.Generator(device=DEV).manual_seed(99)
+    x = torch.randn(1, 256, 256, 256, generator=g, device=DEV, dtype=torch.float32)
+    c = wt.wavedec3(x, "sym4", level=3)
+    assert c[0].shape == (1, 38, 38, 38)
+    assert [lv["aad"].shape[-1] for lv in c[1:]] == [38, 69, 131]
+    want = P.wavedec3(x.cpu(), "sym4", level=3)
+    scale = max(float(t.abs().max()) for t in flatten_coeffs(want))
+    for a, b in zip(flatten_coeffs(c), flatten_coeffs(want)):
+        assert_close_rel(a, b, scale=scale, what="cfg3 coefficients")
+    rec = wt.waverec3(c, "sym4")
+    assert float((rec - x).abs().max()) < 2e-5
+
+
+def test_empty_batch_and_single_sample():
+    x = torch.zeros(0, 32, device=DEV)
+    c = wt.wavedec(x, "db2", level=2)
+    assert [t.shape for t in c] == [torch.Size([0, 10]), torch.Size([0, 10]), torch.Size([0, 17])]
+    one = torch.randn(1, 1, 2, dtype=torch.float64)
+    _cmp_tree(wt.wavedec(one.to(DEV), "haar", mode="zero", level=1), P.wavedec(one, "haar", mode="zero", level=1), "len 2")
+
+
+def test_requires_grad_is_rejected_loudly():
+    x = torch.randn(2, 32, device=DEV, requires_grad=True)
+    with pytest.raises(NotImplementedError):
+        wt.wavedec(x, "haar", level=1)
+    with torch.no_grad():
+        wt.wavedec(x, "haar", level=1)
