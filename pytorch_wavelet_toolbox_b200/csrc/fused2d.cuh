@@ -1,0 +1,417 @@
+// fused2d.cuh -- 2-D analysis level as ONE kernel: rolling column strips on sm_100a.
+//
+// Replaces, per level, the reference's  F.pad -> conv2d(4 x [L x L], stride 2) -> split
+// (src/ptwt/conv_transform_2.py:142-149) by a separable polyphase filter bank that reads the
+// level input once and writes the four sub-bands once:
+//
+//   * a CTA owns a strip of TW output columns and a segment of output rows of one image and
+//     marches down the strip in chunks of CH output rows (2 CH input rows);
+//   * input chunks [2 CH x SW] are staged in shared memory by TMA (cp.async.bulk.tensor, 3-D
+//     tensor map over [batch, H, W], out-of-bounds = zero fill) into an NSTAGE ring, completion
+//     on mbarriers, so the next chunks are in flight while the current one is filtered;
+//     border CTAs patch the out-of-range halo with the boundary extension (ext_index32);
+//   * row pass: lane <-> input row, warp <-> group of 8 output columns; each thread slides the
+//     L-tap window over 2*8+L-2 register-resident samples (LDS.128, conflict-free pitch) and
+//     writes lo/hi rows into a ring of row-filtered lines;
+//   * column pass: lane <-> output column; each thread slides down 4 output rows of the ring and
+//     emits ll, lh, hl, hh -- coalesced 128-byte rows to HBM.  The vertical halo never leaves
+//     shared memory (rolling ring), the horizontal halo costs (L-2)/(2 TW) extra L2 reads.
+//
+// Algorithmic bytes per level: 4 B * (H*W read + 4*Mh*Mw written).
+#pragma once
+
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace wtb {
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers (mbarrier + TMA)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct Fwd2dParams {
+    const T* x;              // level input [batch, H, W]
+    int64_t x_bs, x_rs;      // element strides (batch, row); column stride 1
+    T* out[4];               // k = 0 (approx), 1, 2, 3 (sub-band index of include/wtb200.h)
+    int64_t out_bs[4], out_rs[4];
+    int H, W, Mh, Mw;
+    int seg_rows;            // output rows per segment
+    int mode;
+    int batch0;              // batch offset of this launch (gridDim.z chunking)
+    Taps<T> taps;            // un-flipped dec_lo / dec_hi
+};
+
+template <int L, int TW, int ES = 4>
+struct Fwd2dGeom {
+    static constexpr int HALO = L - 2;
+    // TMA needs the box to start on a 16-byte boundary: the staged tile begins HAL >= HALO columns
+    // left of the first output's window, HAL * ES a multiple of 16 (measured: a misaligned
+    // innermost coordinate traps with "illegal instruction" on sm_100a).
+    static constexpr int HAL = ((HALO * ES + 15) / 16) * 16 / ES;
+    static constexpr int OFF = HAL - HALO;        // columns skipped at the left of the tile
+    static constexpr int CH = 16;                 // output rows per chunk
+    static constexpr int IN_ROWS = 2 * CH;        // input rows per chunk (= 32 = one row per lane)
+    static constexpr int NEED = 2 * TW + HAL;     // input columns staged per strip
+    static constexpr int SW = ((NEED - 4 + 7) / 8) * 8 + 4;  // smem pitch: >= NEED, == 4 (mod 8)
+    static constexpr int MP = TW + 4;             // pitch of the row-filtered ring (== 4 mod 8 for TW % 8 == 0)
+    static constexpr int RING = IN_ROWS + 16;     // ring rows (>= IN_ROWS + HALO)
+    static constexpr int NSTAGE = 2;
+    static constexpr int G = 8;                   // output columns per thread in the row pass
+    static constexpr int NWARP = TW / G;
+    static constexpr int NTHREADS = 32 * NWARP;
+    static constexpr int NV = 2 * G + HAL;        // samples a row-pass thread loads
+    static constexpr int NV4 = (NV + 3) / 4;
+    static_assert(L % 2 == 0 && L >= 2 && L <= 18, "fused path: even filter length <= 18");
+    static_assert(TW % 8 == 0, "TW must be a multiple of 8");
+    static_assert(16 * (NWARP - 1) + 4 * NV4 <= SW, "row pass would read past the staged tile");
+    static_assert(HALO <= 16, "ring too small");
+    static constexpr size_t stage_bytes(size_t es) { return (size_t)IN_ROWS * SW * es; }
+    static constexpr size_t smem_bytes(size_t es) {
+        return NSTAGE * stage_bytes(es) + 2 * (size_t)RING * MP * es + 64;
+    }
+};
+
+template <typename T, int L, int TW, bool USE_TMA>
+__global__ void __launch_bounds__((Fwd2dGeom<L, TW, sizeof(T)>::NTHREADS), 2)
+fwd2d_strip_kernel(const __grid_constant__ Fwd2dParams<T> p, const __grid_constant__ CUtensorMap tmap) {
+    using Gm = Fwd2dGeom<L, TW, sizeof(T)>;
+    constexpr int OFF = Gm::OFF, HAL = Gm::HAL;
+    constexpr int HALO = Gm::HALO, CH = Gm::CH, IN_ROWS = Gm::IN_ROWS, SW = Gm::SW, MP = Gm::MP;
+    constexpr int RING = Gm::RING, NSTAGE = Gm::NSTAGE, G = Gm::G, NT = Gm::NTHREADS, NV4 = Gm::NV4;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* s_in = reinterpret_cast<T*>(smem_raw);                                   // [NSTAGE][IN_ROWS][SW]
+    T* s_lo = reinterpret_cast<T*>(smem_raw + NSTAGE * Gm::stage_bytes(sizeof(T)));  // [RING][MP]
+    T* s_hi = s_lo + RING * MP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_hi + RING * MP);             // [NSTAGE]
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int b = p.batch0 + blockIdx.z;
+    const int x0 = blockIdx.x * TW;                 // first output column of the strip
+    const int y0 = blockIdx.y * p.seg_rows;         // first output row of the segment
+    const int y1 = min(y0 + p.seg_rows, p.Mh);
+    if (y0 >= p.Mh) return;
+    const int yb = y0 - HALO / 2;                   // chunk c covers output rows [yb + CH c, yb + CH (c+1))
+    const int c_in0 = 2 * x0 - HAL;                 // first input column staged (16-byte aligned)
+    const int r_in0 = 2 * yb;                       // first input row of chunk 0
+    const int nchunks = (y1 - yb + CH - 1) / CH;
+    const bool border_x = (c_in0 < 0) || (c_in0 + SW > p.W);
+
+    if (USE_TMA) {
+        if (tid == 0) {
+            tma_prefetch_desc(&tmap);
+            for (int s = 0; s < NSTAGE; ++s) mbar_init(&bars[s], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int s = 0; s < NSTAGE && s < nchunks; ++s) {
+                mbar_expect_tx(&bars[s], (uint32_t)Gm::stage_bytes(sizeof(T)));
+                tma_load_3d(s_in + (size_t)s * IN_ROWS * SW, &tmap, &bars[s], c_in0, r_in0 + s * IN_ROWS, b);
+            }
+        }
+    }
+
+    const T* __restrict__ xb = p.x + (int64_t)b * p.x_bs;
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int stage = c % NSTAGE;
+        T* tile = s_in + (size_t)stage * IN_ROWS * SW;
+        const int r_base = r_in0 + c * IN_ROWS;     // absolute input row of tile row 0
+
+        if (USE_TMA) {
+            mbar_wait(&bars[stage], (uint32_t)((c / NSTAGE) & 1));
+            // border CTAs: replace the zero-filled out-of-range halo by the boundary extension
+            const bool border_y = (r_base < 0) || (r_base + IN_ROWS > p.H);
+            if (p.mode != WT_MODE_ZERO && (border_x || border_y)) {
+                for (int idx = tid; idx < IN_ROWS * SW; idx += NT) {
+                    const int rr = idx / SW, cc = idx - rr * SW;
+                    const int gr = r_base + rr, gc = c_in0 + cc;
+                    if (gr >= 0 && gr < p.H && gc >= 0 && gc < p.W) continue;
+                    const int sr = ext_index32(gr, p.H, p.mode), sc = ext_index32(gc, p.W, p.mode);
+                    tile[idx] = __ldg(xb + (int64_t)sr * p.x_rs + sc);
+                }
+                __syncthreads();
+            }
+        } else {
+            // plain cooperative loader (any alignment): coalesced along columns
+            for (int idx = tid; idx < IN_ROWS * SW; idx += NT) {
+                const int rr = idx / SW, cc = idx - rr * SW;
+                const int sr = ext_index32(r_base + rr, p.H, p.mode), sc = ext_index32(c_in0 + cc, p.W, p.mode);
+                tile[idx] = (sr >= 0 && sc >= 0) ? __ldg(xb + (int64_t)sr * p.x_rs + sc) : T(0);
+            }
+            __syncthreads();
+        }
+
+        // ---------------- row pass: lane <-> tile row, warp <-> 8 output columns -----------------
+        {
+            const T* src = tile + lane * SW + 2 * G * warp;
+            T v[4 * NV4];
+#pragma unroll
+            for (int q = 0; q < NV4; ++q) {
+                if (sizeof(T) == 4) {
+                    const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
+                    v[4 * q + 0] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                } else {
+                    const double2 t0 = *reinterpret_cast<const double2*>(src + 4 * q);
+                    const double2 t1 = *reinterpret_cast<const double2*>(src + 4 * q + 2);
+                    v[4 * q + 0] = t0.x; v[4 * q + 1] = t0.y; v[4 * q + 2] = t1.x; v[4 * q + 3] = t1.y;
+                }
+            }
+            T lo[G], hi[G];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                T a = T(0), h = T(0);
+#pragma unroll
+                for (int k = 0; k < L; ++k) {
+                    a = fma(p.taps.lo[L - 1 - k], v[2 * g + k + OFF], a);
+                    h = fma(p.taps.hi[L - 1 - k], v[2 * g + k + OFF], h);
+                }
+                lo[g] = a; hi[g] = h;
+            }
+            int slot = (c * IN_ROWS + lane) % RING;
+            T* dlo = s_lo + slot * MP + G * warp;
+            T* dhi = s_hi + slot * MP + G * warp;
+            if (sizeof(T) == 4) {
+                *reinterpret_cast<float4*>(dlo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<float4*>(dlo + 4) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                *reinterpret_cast<float4*>(dhi) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4*>(dhi + 4) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; g += 2) {
+                    *reinterpret_cast<double2*>(dlo + g) = make_double2(lo[g], lo[g + 1]);
+                    *reinterpret_cast<double2*>(dhi + g) = make_double2(hi[g], hi[g + 1]);
+                }
+            }
+        }
+        __syncthreads();   // ring rows of this chunk visible; the input stage is free again
+
+        if (USE_TMA && tid == 0 && c + NSTAGE < nchunks) {
+            fence_proxy_async();   // generic-proxy accesses to this stage precede the async refill
+            mbar_expect_tx(&bars[stage], (uint32_t)Gm::stage_bytes(sizeof(T)));
+            tma_load_3d(tile, &tmap, &bars[stage], c_in0, r_in0 + (c + NSTAGE) * IN_ROWS, b);
+        }
+
+        // ---------------- column pass: lane <-> output column, 4 output rows per thread ----------
+        {
+            constexpr int ROWS_PT = 4;
+            constexpr int NGROUP = NT / TW;                  // row groups working concurrently
+            constexpr int NRV = 2 * ROWS_PT + HALO;          // ring rows a thread reads
+            const int cx = tid % TW;
+            for (int rg = tid / TW; rg < CH / ROWS_PT; rg += NGROUP) {
+                const int yl = rg * ROWS_PT;                 // local output row in the chunk
+                // ring row (chunk-local input row index) of the first tap: 2 yl - HALO
+                int slot = (c * IN_ROWS + 2 * yl - HALO + 2 * RING) % RING;
+                T a[NRV], h[NRV];
+#pragma unroll
+                for (int j = 0; j < NRV; ++j) {
+                    a[j] = s_lo[slot * MP + cx];
+                    h[j] = s_hi[slot * MP + cx];
+                    slot = (slot + 1 == RING) ? 0 : slot + 1;
+                }
+                const int gx = x0 + cx;
+#pragma unroll
+                for (int o = 0; o < ROWS_PT; ++o) {
+                    T ll = T(0), lh = T(0), hl = T(0), hh = T(0);
+#pragma unroll
+                    for (int k = 0; k < L; ++k) {
+                        const T tl = p.taps.lo[L - 1 - k], th = p.taps.hi[L - 1 - k];
+                        ll = fma(tl, a[2 * o + k], ll);   // lo_H lo_W
+                        lh = fma(th, a[2 * o + k], lh);   // hi_H lo_W  (k = 2)
+                        hl = fma(tl, h[2 * o + k], hl);   // lo_H hi_W  (k = 1)
+                        hh = fma(th, h[2 * o + k], hh);
+                    }
+                    const int gy = yb + c * CH + yl + o;
+                    if (gy >= y0 && gy < y1 && gx < p.Mw) {
+                        const int64_t bb = (int64_t)b;
+                        p.out[0][bb * p.out_bs[0] + (int64_t)gy * p.out_rs[0] + gx] = ll;
+                        p.out[1][bb * p.out_bs[1] + (int64_t)gy * p.out_rs[1] + gx] = hl;
+                        p.out[2][bb * p.out_bs[2] + (int64_t)gy * p.out_rs[2] + gx] = lh;
+                        p.out[3][bb * p.out_bs[3] + (int64_t)gy * p.out_rs[3] + gx] = hh;
+                    }
+                }
+            }
+        }
+        __syncthreads();   // ring rows may be overwritten by the next chunk's row pass
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled)ptr;
+    });
+    return fn;
+}
+
+template <typename T>
+static bool make_tmap_3d(CUtensorMap* map, const T* base, int64_t B, int64_t H, int64_t W, int64_t bs, int64_t rs,
+                         int box_w, int box_h) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return false;
+    if (((uintptr_t)base & 15) || ((rs * sizeof(T)) & 15) || ((bs * sizeof(T)) & 15)) return false;
+    if (box_w > 256 || box_h > 256 || ((box_w * sizeof(T)) & 15)) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)(rs * sizeof(T)), (cuuint64_t)(bs * sizeof(T))};
+    cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (B == 1) strides[1] = (cuuint64_t)H * strides[0];  // any valid value
+    CUresult r = enc(map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                     (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <typename T, int L, int TW>
+static cudaError_t launch_fwd2d_level(const T* x, int64_t B, int H, int W, int64_t x_bs, int64_t x_rs, T* const out[4],
+                                      const int64_t out_bs[4], const int64_t out_rs[4], int Mh, int Mw, int mode,
+                                      const Taps<T>& taps, cudaStream_t st, uint64_t* launches) {
+    using Gm = Fwd2dGeom<L, TW, sizeof(T)>;
+    Fwd2dParams<T> p;
+    p.x = x; p.x_bs = x_bs; p.x_rs = x_rs;
+    for (int k = 0; k < 4; ++k) { p.out[k] = out[k]; p.out_bs[k] = out_bs[k]; p.out_rs[k] = out_rs[k]; }
+    p.H = H; p.W = W; p.Mh = Mh; p.Mw = Mw; p.mode = mode; p.taps = taps;
+    // segments of 16 k - HALO/2 output rows so that the chunking has no idle tail
+    constexpr int HH = Gm::HALO / 2;
+    int nseg = (Mh + 255) / 256;
+    int seg = ((Mh + nseg - 1) / nseg + HH + 15) / 16 * 16 - HH;
+    if (seg < 16 - HH) seg = 16 - HH;
+    nseg = (Mh + seg - 1) / seg;
+    p.seg_rows = seg;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    const bool tma = make_tmap_3d<T>(&tmap, x, B, H, W, x_bs, x_rs, Gm::SW, Gm::IN_ROWS);
+    const size_t smem = Gm::smem_bytes(sizeof(T));
+    auto kern = tma ? fwd2d_strip_kernel<T, L, TW, true> : fwd2d_strip_kernel<T, L, TW, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int nstrip = (Mw + TW - 1) / TW;
+    for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+        p.batch0 = (int)b0;
+        const int nb = (int)((B - b0) < 65535 ? (B - b0) : 65535);
+        dim3 grid(nstrip, nseg, nb);
+        kern<<<grid, Gm::NTHREADS, smem, st>>>(p, tmap);
+        ++*launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+static bool fused2d_fwd_covers(int ndim, int L) {
+    return ndim == 2 && !(L & 1) && L <= 16 && !getenv("WTB200_DISABLE_FUSED");
+}
+
+// Try the fused path for the first levels of a 2-D analysis; *first_generic receives the number
+// of levels done here (the general path continues from there).
+template <typename T>
+static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* dlo, const double* dhi, const T* x,
+                           int64_t batch, const int64_t* dims, const int64_t* xs, int64_t xbs, const wt_level* lv,
+                           cudaStream_t st, int* first_generic) {
+    *first_generic = 0;
+    if (!fused2d_fwd_covers(ndim, L)) return 0;
+    if (xs[1] != 1) return 0;
+    Taps<T> taps;
+    for (int k = 0; k < L; ++k) { taps.lo[k] = (T)dlo[k]; taps.hi[k] = (T)dhi[k]; }
+    const T* src = x;
+    int64_t sbs = xbs, srs = xs[0];
+    int64_t H = dims[0], W = dims[1];
+    uint64_t launches = 0;
+    for (int l = 0; l < levels; ++l) {
+        const wt_level& d = lv[l];
+        if (H >= (1 << 30) || W >= (1 << 30)) break;
+        if (d.strides[1] != 1 || d.approx_strides[1] != 1) break;
+        T* out[4];
+        int64_t obs[4], ors[4];
+        out[0] = (T*)d.approx; obs[0] = d.approx_batch_stride; ors[0] = d.approx_strides[0];
+        for (int k = 1; k < 4; ++k) {
+            out[k] = (T*)d.details + (int64_t)(k - 1) * d.band_stride;
+            obs[k] = d.details_batch_stride; ors[k] = d.strides[0];
+        }
+        const int Mh = (int)d.dims[0], Mw = (int)d.dims[1];
+        cudaError_t e = cudaSuccess;
+#define WTB_F2D_CASE(LL)                                                                                       \
+    case LL:                                                                                                   \
+        e = launch_fwd2d_level<T, LL, (sizeof(T) == 4 ? 64 : 32)>(src, batch, (int)H, (int)W, sbs, srs, out, obs, ors, Mh, Mw, \
+                                                                  mode, taps, st, &launches);                  \
+        break;
+        switch (L) {
+            WTB_F2D_CASE(2)
+            WTB_F2D_CASE(4)
+            WTB_F2D_CASE(6)
+            WTB_F2D_CASE(8)
+            WTB_F2D_CASE(10)
+            WTB_F2D_CASE(12)
+            WTB_F2D_CASE(14)
+            WTB_F2D_CASE(16)
+            default: return 0;
+        }
+#undef WTB_F2D_CASE
+        g_launches.fetch_add(launches, std::memory_order_relaxed);
+        launches = 0;
+        if (e != cudaSuccess) return cuda_fail(e, "fwd2d_strip_kernel");
+        *first_generic = l + 1;
+        src = out[0]; sbs = obs[0]; srs = ors[0];
+        H = Mh; W = Mw;
+    }
+    return 0;
+}
+
+}  // namespace wtb

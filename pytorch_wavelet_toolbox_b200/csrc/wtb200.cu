@@ -8,6 +8,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -16,9 +17,6 @@
 #include "matrix_generic.cuh"
 #if !defined(WTB_NO_FUSED) && !__has_include("fused2d.cuh")
 #define WTB_NO_FUSED 1
-#endif
-#ifndef WTB_NO_FUSED
-#include "fused2d.cuh"
 #endif
 
 namespace wtb {
@@ -38,6 +36,12 @@ static int cuda_fail(cudaError_t e, const char* what) {
     snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
     return (int)e;
 }
+
+}  // namespace wtb
+#ifndef WTB_NO_FUSED
+#include "fused2d.cuh"
+#endif
+namespace wtb {
 
 static inline int pad_left(int L) { return (2 * L - 3) / 2; }
 
@@ -528,6 +532,13 @@ int64_t wt_coeff_len(int64_t n, int filt_len) { return coeff_len(n, filt_len); }
 size_t wt_dwt_workspace_bytes(int ndim, int dtype, int levels, int filt_len, int64_t batch, const int64_t* dims,
                               int inverse) {
     if (ndim < 1 || ndim > 3 || !dims || levels <= 0) return 0;
+#ifndef WTB_NO_FUSED
+    if (!inverse && fused2d_fwd_covers(ndim, filt_len)) {
+        // the fused path needs no scratch unless it has to bail out (odd strides); keep the
+        // general path's requirement only when the fused path is disabled
+        return 0;
+    }
+#endif
     int64_t s1, s2;
     generic_scratch_elems(ndim, filt_len, batch, dims, inverse, &s1, &s2);
     return (size_t)(s1 + s2) * (dtype == WT_F64 ? 8 : 4);
