@@ -81,10 +81,11 @@ struct Fwd2dParams {
     int seg_rows;            // output rows per segment
     int mode;
     int batch0;              // batch offset of this launch (gridDim.z chunking)
+    int vec_store;           // 1: every output row start is 16-byte aligned -> 128-bit stores
     Taps<T> taps;            // un-flipped dec_lo / dec_hi
 };
 
-template <int L, int TW, int ES = 4>
+template <int L, int TW, int ES = 4, int NSTAGE_ = 2>
 struct Fwd2dGeom {
     static constexpr int HALO = L - 2;
     // TMA needs the box to start on a 16-byte boundary: the staged tile begins HAL >= HALO columns
@@ -97,30 +98,38 @@ struct Fwd2dGeom {
     static constexpr int NEED = 2 * TW + HAL;     // input columns staged per strip
     static constexpr int SW = ((NEED - 4 + 7) / 8) * 8 + 4;  // smem pitch: >= NEED, == 4 (mod 8)
     static constexpr int MP = TW + 4;             // pitch of the row-filtered ring (== 4 mod 8 for TW % 8 == 0)
-    static constexpr int RING = IN_ROWS + 16;     // ring rows (>= IN_ROWS + HALO)
-    static constexpr int NSTAGE = 2;
+    static constexpr int RING = IN_ROWS + HALO;   // ring rows: one chunk plus the vertical halo
+    static constexpr int NSTAGE = NSTAGE_;
     static constexpr int G = 8;                   // output columns per thread in the row pass
     static constexpr int NWARP = TW / G;
     static constexpr int NTHREADS = 32 * NWARP;
     static constexpr int NV = 2 * G + HAL;        // samples a row-pass thread loads
     static constexpr int NV4 = (NV + 3) / 4;
+    static constexpr int VEC = 16 / ES;           // output columns per thread in the column pass
+    static constexpr int NCG = TW / VEC;          // column groups per output row
     static_assert(L % 2 == 0 && L >= 2 && L <= 18, "fused path: even filter length <= 18");
     static_assert(TW % 8 == 0, "TW must be a multiple of 8");
     static_assert(16 * (NWARP - 1) + 4 * NV4 <= SW, "row pass would read past the staged tile");
-    static_assert(HALO <= 16, "ring too small");
     static constexpr size_t stage_bytes(size_t es) { return (size_t)IN_ROWS * SW * es; }
     static constexpr size_t smem_bytes(size_t es) {
         return NSTAGE * stage_bytes(es) + 2 * (size_t)RING * MP * es + 64;
     }
 };
 
-template <typename T, int L, int TW, bool USE_TMA>
-__global__ void __launch_bounds__((Fwd2dGeom<L, TW, sizeof(T)>::NTHREADS), 2)
+template <typename T> struct VecOf;
+template <> struct VecOf<float> { using type = float4; };
+template <> struct VecOf<double> { using type = double2; };
+
+template <typename T, int L, int TW, bool USE_TMA, int NSTG = 2>
+__global__ void __launch_bounds__((Fwd2dGeom<L, TW, sizeof(T), NSTG>::NTHREADS),
+                                  (sizeof(T) == 4 && NSTG == 2 ? (TW == 64 ? 4 : 6) : 2))
 fwd2d_strip_kernel(const __grid_constant__ Fwd2dParams<T> p, const __grid_constant__ CUtensorMap tmap) {
-    using Gm = Fwd2dGeom<L, TW, sizeof(T)>;
+    using Gm = Fwd2dGeom<L, TW, sizeof(T), NSTG>;
+    using V = typename VecOf<T>::type;
     constexpr int OFF = Gm::OFF, HAL = Gm::HAL;
     constexpr int HALO = Gm::HALO, CH = Gm::CH, IN_ROWS = Gm::IN_ROWS, SW = Gm::SW, MP = Gm::MP;
     constexpr int RING = Gm::RING, NSTAGE = Gm::NSTAGE, G = Gm::G, NT = Gm::NTHREADS, NV4 = Gm::NV4;
+    constexpr int VEC = Gm::VEC, NCG = Gm::NCG;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* s_in = reinterpret_cast<T*>(smem_raw);                                   // [NSTAGE][IN_ROWS][SW]
@@ -139,7 +148,8 @@ fwd2d_strip_kernel(const __grid_constant__ Fwd2dParams<T> p, const __grid_consta
     const int c_in0 = 2 * x0 - HAL;                 // first input column staged (16-byte aligned)
     const int r_in0 = 2 * yb;                       // first input row of chunk 0
     const int nchunks = (y1 - yb + CH - 1) / CH;
-    const bool border_x = (c_in0 < 0) || (c_in0 + SW > p.W);
+    const int c_need1 = 2 * min(x0 + TW, p.Mw);      // one past the last input column any output reads
+    const int r_need1 = 2 * y1;                      // one past the last input row any output reads
 
     if (USE_TMA) {
         if (tid == 0) {
@@ -149,7 +159,11 @@ fwd2d_strip_kernel(const __grid_constant__ Fwd2dParams<T> p, const __grid_consta
         }
         __syncthreads();
         if (tid == 0) {
-            for (int s = 0; s < NSTAGE && s < nchunks; ++s) {
+            // NSTAGE == 2: both stages are filled up front and a stage is refilled once its chunk has
+            // been row-filtered.  NSTAGE > 2: NSTAGE-1 loads stay in flight all the time -- the load of
+            // chunk c + NSTAGE - 1 is issued at the top of iteration c into the stage chunk c - 1 used.
+            constexpr int PRE = NSTAGE == 2 ? 2 : NSTAGE - 1;
+            for (int s = 0; s < PRE && s < nchunks; ++s) {
                 mbar_expect_tx(&bars[s], (uint32_t)Gm::stage_bytes(sizeof(T)));
                 tma_load_3d(s_in + (size_t)s * IN_ROWS * SW, &tmap, &bars[s], c_in0, r_in0 + s * IN_ROWS, b);
             }
@@ -158,24 +172,56 @@ fwd2d_strip_kernel(const __grid_constant__ Fwd2dParams<T> p, const __grid_consta
 
     const T* __restrict__ xb = p.x + (int64_t)b * p.x_bs;
 
+    // column-pass work decomposition (fixed per thread when NT == 2 * (CH/2) * NCG)
+    constexpr int CP_ITEMS = 2 * (CH / 2) * NCG;    // (array half) x (row pair) x (column group)
+
+    int ring_base = 0;                              // ring row that holds tile row 0 of the current chunk
     for (int c = 0; c < nchunks; ++c) {
         const int stage = c % NSTAGE;
         T* tile = s_in + (size_t)stage * IN_ROWS * SW;
         const int r_base = r_in0 + c * IN_ROWS;     // absolute input row of tile row 0
 
         if (USE_TMA) {
+            if (NSTAGE > 2 && tid == 0 && c + NSTAGE - 1 < nchunks) {
+                const int cn = c + NSTAGE - 1, sn = cn % NSTAGE;
+                fence_proxy_async();
+                mbar_expect_tx(&bars[sn], (uint32_t)Gm::stage_bytes(sizeof(T)));
+                tma_load_3d(s_in + (size_t)sn * IN_ROWS * SW, &tmap, &bars[sn], c_in0, r_in0 + cn * IN_ROWS, b);
+            }
             mbar_wait(&bars[stage], (uint32_t)((c / NSTAGE) & 1));
-            // border CTAs: replace the zero-filled out-of-range halo by the boundary extension
-            const bool border_y = (r_base < 0) || (r_base + IN_ROWS > p.H);
-            if (p.mode != WT_MODE_ZERO && (border_x || border_y)) {
-                for (int idx = tid; idx < IN_ROWS * SW; idx += NT) {
-                    const int rr = idx / SW, cc = idx - rr * SW;
-                    const int gr = r_base + rr, gc = c_in0 + cc;
-                    if (gr >= 0 && gr < p.H && gc >= 0 && gc < p.W) continue;
-                    const int sr = ext_index32(gr, p.H, p.mode), sc = ext_index32(gc, p.W, p.mode);
-                    tile[idx] = __ldg(xb + (int64_t)sr * p.x_rs + sc);
+            // border CTAs: replace the zero-filled out-of-range halo by the boundary extension.
+            // Only the samples some output of this strip / segment really reads are patched:
+            // tile columns [0, nl) and [cr0, cr1) of the in-range rows, and tile columns [0, cr1)
+            // of the out-of-range rows [0, nt) and [rb0, rb1).
+            if (p.mode != WT_MODE_ZERO) {
+                const int nl = c_in0 < 0 ? -c_in0 : 0;
+                const int cr1 = c_need1 - c_in0;                    // one past the last needed tile column
+                const int cr0 = max(min(p.W - c_in0, cr1), nl);
+                const int nt = r_base < 0 ? min(-r_base, IN_ROWS) : 0;
+                const int rb1 = min(r_need1 - r_base, IN_ROWS);     // one past the last needed tile row
+                const int rb0 = max(min(p.H - r_base, rb1), nt);
+                const int wb = nl + (cr1 - cr0);
+                const bool patch = (wb > 0) || (nt > 0) || (rb1 > rb0);
+                if (patch) {
+                    const int n_in = rb0 - nt;                      // in-range tile rows [nt, rb0)
+                    for (int idx = tid; idx < n_in * wb; idx += NT) {
+                        const int rr = nt + idx / wb, q = idx % wb;
+                        const int cc = q < nl ? q : cr0 + (q - nl);
+                        const int sc = ext_index32(c_in0 + cc, p.W, p.mode);
+                        tile[rr * SW + cc] = __ldg(xb + (int64_t)(r_base + rr) * p.x_rs + sc);
+                    }
+                    const int n_oob = nt + (rb1 - rb0);
+                    if (n_oob > 0 && cr1 > 0) {
+                        for (int idx = tid; idx < n_oob * cr1; idx += NT) {
+                            const int q = idx / cr1, cc = idx % cr1;
+                            const int rr = q < nt ? q : rb0 + (q - nt);
+                            const int sr = ext_index32(r_base + rr, p.H, p.mode);
+                            const int sc = ext_index32(c_in0 + cc, p.W, p.mode);
+                            tile[rr * SW + cc] = __ldg(xb + (int64_t)sr * p.x_rs + sc);
+                        }
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
             }
         } else {
             // plain cooperative loader (any alignment): coalesced along columns
@@ -213,7 +259,8 @@ fwd2d_strip_kernel(const __grid_constant__ Fwd2dParams<T> p, const __grid_consta
                 }
                 lo[g] = a; hi[g] = h;
             }
-            int slot = (c * IN_ROWS + lane) % RING;
+            int slot = ring_base + lane;              // ring row of this tile row
+            if (slot >= RING) slot -= RING;
             T* dlo = s_lo + slot * MP + G * warp;
             T* dhi = s_hi + slot * MP + G * warp;
             if (sizeof(T) == 4) {
@@ -231,53 +278,87 @@ fwd2d_strip_kernel(const __grid_constant__ Fwd2dParams<T> p, const __grid_consta
         }
         __syncthreads();   // ring rows of this chunk visible; the input stage is free again
 
-        if (USE_TMA && tid == 0 && c + NSTAGE < nchunks) {
+        if (USE_TMA && NSTAGE == 2 && tid == 0 && c + NSTAGE < nchunks) {
             fence_proxy_async();   // generic-proxy accesses to this stage precede the async refill
             mbar_expect_tx(&bars[stage], (uint32_t)Gm::stage_bytes(sizeof(T)));
             tma_load_3d(tile, &tmap, &bars[stage], c_in0, r_in0 + (c + NSTAGE) * IN_ROWS, b);
         }
 
-        // ---------------- column pass: lane <-> output column, 4 output rows per thread ----------
+        // ------- column pass: thread <-> (lo|hi array, 2 output rows, VEC output columns) --------
+        // the lo array yields bands k = 0 (lo_H) and k = 2 (hi_H); the hi array k = 1 and k = 3
         {
-            constexpr int ROWS_PT = 4;
-            constexpr int NGROUP = NT / TW;                  // row groups working concurrently
-            constexpr int NRV = 2 * ROWS_PT + HALO;          // ring rows a thread reads
-            const int cx = tid % TW;
-            for (int rg = tid / TW; rg < CH / ROWS_PT; rg += NGROUP) {
-                const int yl = rg * ROWS_PT;                 // local output row in the chunk
-                // ring row (chunk-local input row index) of the first tap: 2 yl - HALO
-                int slot = (c * IN_ROWS + 2 * yl - HALO + 2 * RING) % RING;
-                T a[NRV], h[NRV];
+            const int gy_chunk = yb + c * CH;
+            for (int item = tid; item < CP_ITEMS; item += NT) {
+                const int half = item / (CP_ITEMS / 2);
+                const int rem = item - half * (CP_ITEMS / 2);
+                const int rp = rem / NCG, cg = rem - rp * NCG;
+                const int yl = 2 * rp;
+                const T* ring = (half ? s_hi : s_lo) + VEC * cg;
+                int row0 = ring_base + 2 * yl - HALO;               // ring row of the first tap
+                if (row0 < 0) row0 += RING;
+                T accL[2][VEC], accH[2][VEC];
 #pragma unroll
-                for (int j = 0; j < NRV; ++j) {
-                    a[j] = s_lo[slot * MP + cx];
-                    h[j] = s_hi[slot * MP + cx];
-                    slot = (slot + 1 == RING) ? 0 : slot + 1;
-                }
-                const int gx = x0 + cx;
+                for (int r = 0; r < 2; ++r)
 #pragma unroll
-                for (int o = 0; o < ROWS_PT; ++o) {
-                    T ll = T(0), lh = T(0), hl = T(0), hh = T(0);
+                    for (int e = 0; e < VEC; ++e) { accL[r][e] = T(0); accH[r][e] = T(0); }
 #pragma unroll
-                    for (int k = 0; k < L; ++k) {
-                        const T tl = p.taps.lo[L - 1 - k], th = p.taps.hi[L - 1 - k];
-                        ll = fma(tl, a[2 * o + k], ll);   // lo_H lo_W
-                        lh = fma(th, a[2 * o + k], lh);   // hi_H lo_W  (k = 2)
-                        hl = fma(tl, h[2 * o + k], hl);   // lo_H hi_W  (k = 1)
-                        hh = fma(th, h[2 * o + k], hh);
+                for (int j = 0; j < L + 2; ++j) {
+                    int rj = row0 + j;
+                    if (rj >= RING) rj -= RING;
+                    const V t = *reinterpret_cast<const V*>(ring + rj * MP);
+                    T w[VEC];
+                    if (sizeof(T) == 4) {
+                        const float4 f = *reinterpret_cast<const float4*>(&t);
+                        w[0] = f.x; w[1] = f.y; w[VEC > 2 ? 2 : 0] = f.z; w[VEC > 2 ? 3 : 1] = f.w;
+                    } else {
+                        const double2 f = *reinterpret_cast<const double2*>(&t);
+                        w[0] = f.x; w[1] = f.y;
                     }
-                    const int gy = yb + c * CH + yl + o;
-                    if (gy >= y0 && gy < y1 && gx < p.Mw) {
-                        const int64_t bb = (int64_t)b;
-                        p.out[0][bb * p.out_bs[0] + (int64_t)gy * p.out_rs[0] + gx] = ll;
-                        p.out[1][bb * p.out_bs[1] + (int64_t)gy * p.out_rs[1] + gx] = hl;
-                        p.out[2][bb * p.out_bs[2] + (int64_t)gy * p.out_rs[2] + gx] = lh;
-                        p.out[3][bb * p.out_bs[3] + (int64_t)gy * p.out_rs[3] + gx] = hh;
+                    if (j < L) {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) {
+                            accL[0][e] = fma(p.taps.lo[L - 1 - j], w[e], accL[0][e]);
+                            accH[0][e] = fma(p.taps.hi[L - 1 - j], w[e], accH[0][e]);
+                        }
+                    }
+                    if (j >= 2) {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) {
+                            accL[1][e] = fma(p.taps.lo[L + 1 - j], w[e], accL[1][e]);
+                            accH[1][e] = fma(p.taps.hi[L + 1 - j], w[e], accH[1][e]);
+                        }
+                    }
+                }
+                const int gx = x0 + VEC * cg;
+                if (gx >= p.Mw) continue;
+                T* oL = p.out[half] + (int64_t)b * p.out_bs[half] + gx;          // vertical low-pass
+                T* oH = p.out[2 + half] + (int64_t)b * p.out_bs[2 + half] + gx;  // vertical high-pass
+                const int64_t rsL = p.out_rs[half], rsH = p.out_rs[2 + half];
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int gy = gy_chunk + yl + r;
+                    if (gy < y0 || gy >= y1) continue;
+                    T* dl = oL + (int64_t)gy * rsL;
+                    T* dh = oH + (int64_t)gy * rsH;
+                    if (p.vec_store) {
+                        if (sizeof(T) == 4) {
+                            *reinterpret_cast<float4*>(dl) = make_float4(accL[r][0], accL[r][1], accL[r][VEC > 2 ? 2 : 0], accL[r][VEC > 2 ? 3 : 1]);
+                            *reinterpret_cast<float4*>(dh) = make_float4(accH[r][0], accH[r][1], accH[r][VEC > 2 ? 2 : 0], accH[r][VEC > 2 ? 3 : 1]);
+                        } else {
+                            *reinterpret_cast<double2*>(dl) = make_double2(accL[r][0], accL[r][1]);
+                            *reinterpret_cast<double2*>(dh) = make_double2(accH[r][0], accH[r][1]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e)
+                            if (gx + e < p.Mw) { dl[e] = accL[r][e]; dh[e] = accH[r][e]; }
                     }
                 }
             }
         }
         __syncthreads();   // ring rows may be overwritten by the next chunk's row pass
+        ring_base += IN_ROWS;
+        if (ring_base >= RING) ring_base -= RING;
     }
 }
 
@@ -319,15 +400,23 @@ static bool make_tmap_3d(CUtensorMap* map, const T* base, int64_t B, int64_t H, 
     return r == CUDA_SUCCESS;
 }
 
-template <typename T, int L, int TW>
+template <typename T, int L, int TW, int NSTG = 2>
 static cudaError_t launch_fwd2d_level(const T* x, int64_t B, int H, int W, int64_t x_bs, int64_t x_rs, T* const out[4],
                                       const int64_t out_bs[4], const int64_t out_rs[4], int Mh, int Mw, int mode,
                                       const Taps<T>& taps, cudaStream_t st, uint64_t* launches) {
-    using Gm = Fwd2dGeom<L, TW, sizeof(T)>;
+    using Gm = Fwd2dGeom<L, TW, sizeof(T), NSTG>;
     Fwd2dParams<T> p;
     p.x = x; p.x_bs = x_bs; p.x_rs = x_rs;
     for (int k = 0; k < 4; ++k) { p.out[k] = out[k]; p.out_bs[k] = out_bs[k]; p.out_rs[k] = out_rs[k]; }
     p.H = H; p.W = W; p.Mh = Mh; p.Mw = Mw; p.mode = mode; p.taps = taps;
+    // 128-bit stores need every band row to start on a 16-byte boundary and the row pitch to
+    // cover the rounded-up width (the packed layout of the Python side guarantees both)
+    constexpr int VEC = 16 / (int)sizeof(T);
+    p.vec_store = 1;
+    for (int k = 0; k < 4; ++k) {
+        if (((uintptr_t)out[k] & 15) || (out_bs[k] % VEC) || (out_rs[k] % VEC) || out_rs[k] < (Mw + VEC - 1) / VEC * VEC)
+            p.vec_store = 0;
+    }
     // segments of 16 k - HALO/2 output rows so that the chunking has no idle tail
     constexpr int HH = Gm::HALO / 2;
     int nseg = (Mh + 255) / 256;
@@ -339,7 +428,7 @@ static cudaError_t launch_fwd2d_level(const T* x, int64_t B, int H, int W, int64
     memset(&tmap, 0, sizeof(tmap));
     const bool tma = make_tmap_3d<T>(&tmap, x, B, H, W, x_bs, x_rs, Gm::SW, Gm::IN_ROWS);
     const size_t smem = Gm::smem_bytes(sizeof(T));
-    auto kern = tma ? fwd2d_strip_kernel<T, L, TW, true> : fwd2d_strip_kernel<T, L, TW, false>;
+    auto kern = tma ? fwd2d_strip_kernel<T, L, TW, true, NSTG> : fwd2d_strip_kernel<T, L, TW, false, NSTG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int nstrip = (Mw + TW - 1) / TW;
@@ -374,6 +463,8 @@ static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* 
     int64_t sbs = xbs, srs = xs[0];
     int64_t H = dims[0], W = dims[1];
     uint64_t launches = 0;
+    const char* ev = getenv("WTB200_FWD2D_VARIANT");
+    const int variant = ev ? atoi(ev) : 0;
     for (int l = 0; l < levels; ++l) {
         const wt_level& d = lv[l];
         if (H >= (1 << 30) || W >= (1 << 30)) break;
@@ -389,8 +480,15 @@ static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* 
         cudaError_t e = cudaSuccess;
 #define WTB_F2D_CASE(LL)                                                                                       \
     case LL:                                                                                                   \
-        e = launch_fwd2d_level<T, LL, (sizeof(T) == 4 ? 64 : 32)>(src, batch, (int)H, (int)W, sbs, srs, out, obs, ors, Mh, Mw, \
-                                                                  mode, taps, st, &launches);                  \
+        if (variant == 1)                                                                                      \
+            e = launch_fwd2d_level<T, LL, (sizeof(T) == 4 ? 64 : 32), 3>(src, batch, (int)H, (int)W, sbs, srs, out, obs, ors, \
+                                                                         Mh, Mw, mode, taps, st, &launches);   \
+        else if (variant == 2)                                                                                 \
+            e = launch_fwd2d_level<T, LL, 32, 2>(src, batch, (int)H, (int)W, sbs, srs, out, obs, ors,             \
+                                                 Mh, Mw, mode, taps, st, &launches);                           \
+        else                                                                                                   \
+            e = launch_fwd2d_level<T, LL, (sizeof(T) == 4 ? 64 : 32), 2>(src, batch, (int)H, (int)W, sbs, srs, out, obs, ors, \
+                                                                         Mh, Mw, mode, taps, st, &launches);   \
         break;
         switch (L) {
             WTB_F2D_CASE(2)
