@@ -69,6 +69,63 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 }
 
 // ------------------------------------------------------------------------------------------
+// packed-FP32 filter helpers (FFMA2 = fma.rn.f32x2, one issue slot for two FMAs on sm_100a)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(const float2 a, const float2 b, const float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(*reinterpret_cast<unsigned long long*>(&d))
+        : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)),
+          "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+    return d;
+}
+
+// Row filter of one thread: 8 consecutive (lo, hi) outputs from the register window v[].
+// out[g] = sum_k dec[L-1-k] v[2g+k+OFF], evaluated as an even-tap and an odd-tap partial sum in the
+// two halves of one FFMA2 accumulator.
+template <int L, int OFF, int NV>
+__device__ __forceinline__ void row_filter8(const float (&v)[NV], const float2* __restrict__ pl,
+                                            const float2* __restrict__ ph, float (&lo)[8], float (&hi)[8]) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+        float2 a = make_float2(0.f, 0.f), h = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < L / 2; ++m) {
+            const float2 x = make_float2(v[2 * g + 2 * m + OFF], v[2 * g + 2 * m + OFF + 1]);
+            a = ffma2(pl[m], x, a);
+            h = ffma2(ph[m], x, h);
+        }
+        lo[g] = a.x + a.y;
+        hi[g] = h.x + h.y;
+    }
+}
+
+// Column filter of one thread: 2 output rows x 4 columns from L+2 consecutive ring rows (no wrap:
+// the ring carries mirror rows), vertical low-pass into accL, high-pass into accH.
+template <int L>
+__device__ __forceinline__ void col_filter2x4(const float* __restrict__ rows, int pitch, const float2* __restrict__ bl,
+                                              const float2* __restrict__ bh, float2 (&accL)[2][2], float2 (&accH)[2][2]) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { accL[r][e] = make_float2(0.f, 0.f); accH[r][e] = make_float2(0.f, 0.f); }
+#pragma unroll
+    for (int j = 0; j < L + 2; ++j) {
+        const float4 f = *reinterpret_cast<const float4*>(rows + j * pitch);
+        const float2 w0 = make_float2(f.x, f.y), w1 = make_float2(f.z, f.w);
+        if (j < L) {
+            accL[0][0] = ffma2(bl[j], w0, accL[0][0]); accL[0][1] = ffma2(bl[j], w1, accL[0][1]);
+            accH[0][0] = ffma2(bh[j], w0, accH[0][0]); accH[0][1] = ffma2(bh[j], w1, accH[0][1]);
+        }
+        if (j >= 2) {
+            accL[1][0] = ffma2(bl[j - 2], w0, accL[1][0]); accL[1][1] = ffma2(bl[j - 2], w1, accL[1][1]);
+            accH[1][0] = ffma2(bh[j - 2], w0, accH[1][0]); accH[1][1] = ffma2(bh[j - 2], w1, accH[1][1]);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------
 // kernel
 // ------------------------------------------------------------------------------------------
 template <typename T>
@@ -83,6 +140,8 @@ struct Fwd2dParams {
     int batch0;              // batch offset of this launch (gridDim.z chunking)
     int vec_store;           // 1: every output row start is 16-byte aligned -> 128-bit stores
     Taps<T> taps;            // un-flipped dec_lo / dec_hi
+    // float32 fast kernel: taps packed for FFMA2 (see row_filter8 / col_filter2x4)
+    float2 pl[8], ph[8], bl[16], bh[16];
 };
 
 template <int L, int TW, int ES = 4, int NSTAGE_ = 2>
@@ -363,6 +422,189 @@ fwd2d_strip_kernel(const __grid_constant__ Fwd2dParams<T> p, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
+// float32 fast variant: same structure as fwd2d_strip_kernel, with packed FP32 FMAs (FFMA2), mirror
+// rows behind the ring (column-pass windows never wrap, so their loads use immediate offsets) and
+// all per-thread index arithmetic hoisted out of the chunk loop.
+// ------------------------------------------------------------------------------------------
+template <int L, int TW>
+struct Fwd2dGeomF {
+    using Base = Fwd2dGeom<L, TW, 4, 2>;
+    static constexpr int MIR = L + 2;
+    static constexpr size_t SMEM = 2 * Base::stage_bytes(4) + 2 * (size_t)(Base::RING + MIR) * Base::MP * 4 + 64;
+};
+
+template <int L, int TW, bool USE_TMA>
+__global__ void __launch_bounds__((Fwd2dGeom<L, TW, 4, 2>::NTHREADS), 3)
+fwd2d_strip_f32_kernel(const __grid_constant__ Fwd2dParams<float> p, const __grid_constant__ CUtensorMap tmap) {
+    using Gm = Fwd2dGeom<L, TW, 4, 2>;
+    constexpr int OFF = Gm::OFF, HAL = Gm::HAL, HALO = Gm::HALO, CH = Gm::CH, IN_ROWS = Gm::IN_ROWS, SW = Gm::SW;
+    constexpr int MP = Gm::MP, RING = Gm::RING, NT = Gm::NTHREADS, NV4 = Gm::NV4, MIR = Fwd2dGeomF<L, TW>::MIR;
+    constexpr int NCG = TW / 4;
+    static_assert(NT == 2 * (CH / 2) * NCG, "one column-pass item per thread");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_in = reinterpret_cast<float*>(smem_raw);                          // [2][IN_ROWS][SW]
+    float* s_lo = s_in + 2 * IN_ROWS * SW;                                     // [RING + MIR][MP]
+    float* s_hi = s_lo + (RING + MIR) * MP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_hi + (RING + MIR) * MP);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = p.batch0 + blockIdx.z;
+    const int x0 = blockIdx.x * TW;
+    const int y0 = blockIdx.y * p.seg_rows;
+    if (y0 >= p.Mh) return;
+    const int y1 = min(y0 + p.seg_rows, p.Mh);
+    const int yb = y0 - HALO / 2;
+    const int c_in0 = 2 * x0 - HAL;
+    const int r_in0 = 2 * yb;
+    const int nchunks = (y1 - yb + CH - 1) / CH;
+    const int c_need1 = 2 * min(x0 + TW, p.Mw);
+    const int r_need1 = 2 * y1;
+
+    if (USE_TMA) {
+        if (tid == 0) {
+            tma_prefetch_desc(&tmap);
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int s = 0; s < 2 && s < nchunks; ++s) {
+                mbar_expect_tx(&bars[s], (uint32_t)Gm::stage_bytes(4));
+                tma_load_3d(s_in + s * IN_ROWS * SW, &tmap, &bars[s], c_in0, r_in0 + s * IN_ROWS, b);
+            }
+        }
+    }
+    const float* __restrict__ xb = p.x + (int64_t)b * p.x_bs;
+
+    // per-thread constants of the column pass: (lo|hi array, row pair, 4-column group)
+    const int half = tid / (NT / 2);
+    const int rem = tid - half * (NT / 2);
+    const int rp = rem / NCG, cg = rem - rp * NCG;
+    const int yl = 2 * rp;
+    const float* cring = (half ? s_hi : s_lo) + 4 * cg;
+    const int gx = x0 + 4 * cg;
+    const bool col_ok = gx < p.Mw;
+    // bands: the lo array yields k = 0 (vertical low) and k = 2 (vertical high); the hi array k = 1, 3
+    float* pL = p.out[half] + (int64_t)b * p.out_bs[half] + (int64_t)(yb + yl) * p.out_rs[half] + gx;
+    float* pH = p.out[2 + half] + (int64_t)b * p.out_bs[2 + half] + (int64_t)(yb + yl) * p.out_rs[2 + half] + gx;
+    const int64_t rsL = p.out_rs[half], rsH = p.out_rs[2 + half];
+
+    int ring_base = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int stage = c & 1;
+        float* tile = s_in + stage * IN_ROWS * SW;
+        const int r_base = r_in0 + c * IN_ROWS;
+
+        if (USE_TMA) {
+            mbar_wait(&bars[stage], (uint32_t)((c >> 1) & 1));
+            if (p.mode != WT_MODE_ZERO) {
+                const int nl = c_in0 < 0 ? -c_in0 : 0;
+                const int cr1 = min(c_need1 - c_in0, SW);
+                const int cr0 = max(min(p.W - c_in0, cr1), nl);
+                const int nt = r_base < 0 ? min(-r_base, IN_ROWS) : 0;
+                const int rb1 = min(r_need1 - r_base, IN_ROWS);
+                const int rb0 = max(min(p.H - r_base, rb1), nt);
+                const int wb = nl + (cr1 - cr0);
+                const bool patch = (wb > 0) || (nt > 0) || (rb1 > rb0);
+                if (patch) {
+                    const int n_in = rb0 - nt;
+                    for (int idx = tid; idx < n_in * wb; idx += NT) {
+                        const int rr = nt + idx / wb, q = idx % wb;
+                        const int cc = q < nl ? q : cr0 + (q - nl);
+                        const int sc = ext_index32(c_in0 + cc, p.W, p.mode);
+                        tile[rr * SW + cc] = __ldg(xb + (int64_t)(r_base + rr) * p.x_rs + sc);
+                    }
+                    const int n_oob = nt + (rb1 - rb0);
+                    if (n_oob > 0 && cr1 > 0) {
+                        for (int idx = tid; idx < n_oob * cr1; idx += NT) {
+                            const int q = idx / cr1, cc = idx % cr1;
+                            const int rr = q < nt ? q : rb0 + (q - nt);
+                            const int sr = ext_index32(r_base + rr, p.H, p.mode);
+                            const int sc = ext_index32(c_in0 + cc, p.W, p.mode);
+                            tile[rr * SW + cc] = __ldg(xb + (int64_t)sr * p.x_rs + sc);
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        } else {
+            for (int idx = tid; idx < IN_ROWS * SW; idx += NT) {
+                const int rr = idx / SW, cc = idx - rr * SW;
+                const int sr = ext_index32(r_base + rr, p.H, p.mode), sc = ext_index32(c_in0 + cc, p.W, p.mode);
+                tile[idx] = (sr >= 0 && sc >= 0) ? __ldg(xb + (int64_t)sr * p.x_rs + sc) : 0.f;
+            }
+            __syncthreads();
+        }
+
+        // ---- row pass ---------------------------------------------------------------------------
+        {
+            const float* src = tile + lane * SW + 16 * warp;
+            float v[4 * NV4];
+#pragma unroll
+            for (int q = 0; q < NV4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+            float lo[8], hi[8];
+            row_filter8<L, OFF>(v, p.pl, p.ph, lo, hi);
+            int slot = ring_base + lane;
+            if (slot >= RING) slot -= RING;
+            float* dlo = s_lo + slot * MP + 8 * warp;
+            float* dhi = s_hi + slot * MP + 8 * warp;
+            const float4 l0 = make_float4(lo[0], lo[1], lo[2], lo[3]), l1 = make_float4(lo[4], lo[5], lo[6], lo[7]);
+            const float4 h0 = make_float4(hi[0], hi[1], hi[2], hi[3]), h1 = make_float4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<float4*>(dlo) = l0; *reinterpret_cast<float4*>(dlo + 4) = l1;
+            *reinterpret_cast<float4*>(dhi) = h0; *reinterpret_cast<float4*>(dhi + 4) = h1;
+            if (slot < MIR) {
+                *reinterpret_cast<float4*>(dlo + RING * MP) = l0; *reinterpret_cast<float4*>(dlo + RING * MP + 4) = l1;
+                *reinterpret_cast<float4*>(dhi + RING * MP) = h0; *reinterpret_cast<float4*>(dhi + RING * MP + 4) = h1;
+            }
+        }
+        __syncthreads();
+
+        if (USE_TMA && tid == 0 && c + 2 < nchunks) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[stage], (uint32_t)Gm::stage_bytes(4));
+            tma_load_3d(tile, &tmap, &bars[stage], c_in0, r_in0 + (c + 2) * IN_ROWS, b);
+        }
+
+        // ---- column pass --------------------------------------------------------------------------
+        {
+            int row0 = ring_base + 2 * yl - HALO;
+            if (row0 < 0) row0 += RING;
+            else if (row0 >= RING) row0 -= RING;
+            float2 accL[2][2], accH[2][2];
+            col_filter2x4<L>(cring + row0 * MP, MP, p.bl, p.bh, accL, accH);
+            if (col_ok) {
+                const int gyc = yb + c * CH + yl;
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const int gy = gyc + r;
+                    if (gy < y0 || gy >= y1) continue;
+                    float* dl = pL + (int64_t)(c * CH + r) * rsL;
+                    float* dh = pH + (int64_t)(c * CH + r) * rsH;
+                    if (p.vec_store) {
+                        *reinterpret_cast<float4*>(dl) = make_float4(accL[r][0].x, accL[r][0].y, accL[r][1].x, accL[r][1].y);
+                        *reinterpret_cast<float4*>(dh) = make_float4(accH[r][0].x, accH[r][0].y, accH[r][1].x, accH[r][1].y);
+                    } else {
+                        const float aL[4] = {accL[r][0].x, accL[r][0].y, accL[r][1].x, accL[r][1].y};
+                        const float aH[4] = {accH[r][0].x, accH[r][0].y, accH[r][1].x, accH[r][1].y};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (gx + e < p.Mw) { dl[e] = aL[e]; dh[e] = aH[e]; }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        ring_base += IN_ROWS;
+        if (ring_base >= RING) ring_base -= RING;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -420,6 +662,10 @@ static cudaError_t launch_fwd2d_level(const T* x, int64_t B, int H, int W, int64
     // segments of 16 k - HALO/2 output rows so that the chunking has no idle tail
     constexpr int HH = Gm::HALO / 2;
     int nseg = (Mh + 255) / 256;
+    {   // small levels: shorter segments so that the grid still fills the machine a few times
+        const int64_t nstrip0 = (Mw + TW - 1) / TW;
+        while (nseg * nstrip0 * B < 4 * 592 && (Mh + nseg - 1) / nseg > 48) ++nseg;
+    }
     int seg = ((Mh + nseg - 1) / nseg + HH + 15) / 16 * 16 - HH;
     if (seg < 16 - HH) seg = 16 - HH;
     nseg = (Mh + seg - 1) / seg;
@@ -427,8 +673,22 @@ static cudaError_t launch_fwd2d_level(const T* x, int64_t B, int H, int W, int64
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     const bool tma = make_tmap_3d<T>(&tmap, x, B, H, W, x_bs, x_rs, Gm::SW, Gm::IN_ROWS);
-    const size_t smem = Gm::smem_bytes(sizeof(T));
+    size_t smem = Gm::smem_bytes(sizeof(T));
     auto kern = tma ? fwd2d_strip_kernel<T, L, TW, true, NSTG> : fwd2d_strip_kernel<T, L, TW, false, NSTG>;
+    if constexpr (sizeof(T) == 4 && TW == 64 && NSTG == 2) {
+        if (!getenv("WTB200_NO_FFMA2")) {
+            for (int m = 0; m < L / 2; ++m) {
+                p.pl[m] = make_float2(taps.lo[L - 1 - 2 * m], taps.lo[L - 2 - 2 * m]);
+                p.ph[m] = make_float2(taps.hi[L - 1 - 2 * m], taps.hi[L - 2 - 2 * m]);
+            }
+            for (int j = 0; j < L; ++j) {
+                p.bl[j] = make_float2(taps.lo[L - 1 - j], taps.lo[L - 1 - j]);
+                p.bh[j] = make_float2(taps.hi[L - 1 - j], taps.hi[L - 1 - j]);
+            }
+            kern = tma ? fwd2d_strip_f32_kernel<L, TW, true> : fwd2d_strip_f32_kernel<L, TW, false>;
+            smem = Fwd2dGeomF<L, TW>::SMEM;
+        }
+    }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int nstrip = (Mw + TW - 1) / TW;
@@ -442,6 +702,32 @@ static cudaError_t launch_fwd2d_level(const T* x, int64_t B, int H, int W, int64
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+template <int L>
+static cudaError_t launch_fwd2d_pair(const float* x, int64_t B, int H, int W, int64_t x_bs, int64_t x_rs,
+                                     const wt_level& l1, const wt_level& l2, int mode, const Taps<float>& taps,
+                                     cudaStream_t st, uint64_t* launches);
+static bool pair2d_supported(int L, int mode);
+
+template <typename T>
+static bool try_pair(const T*, int64_t, int, int, int64_t, int64_t, const wt_level&, const wt_level&, int, int,
+                     const Taps<T>&, cudaStream_t, uint64_t*, cudaError_t*) {
+    return false;
+}
+template <>
+bool try_pair<float>(const float* x, int64_t B, int H, int W, int64_t x_bs, int64_t x_rs, const wt_level& l1,
+                     const wt_level& l2, int L, int mode, const Taps<float>& taps, cudaStream_t st,
+                     uint64_t* launches, cudaError_t* err) {
+    if (!pair2d_supported(L, mode)) return false;
+    if (l1.strides[1] != 1 || l2.strides[1] != 1 || l2.approx_strides[1] != 1) return false;
+    switch (L) {
+        case 2: *err = launch_fwd2d_pair<2>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches); return true;
+        case 4: *err = launch_fwd2d_pair<4>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches); return true;
+        case 6: *err = launch_fwd2d_pair<6>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches); return true;
+        case 8: *err = launch_fwd2d_pair<8>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches); return true;
+        default: return false;
+    }
 }
 
 static bool fused2d_fwd_covers(int ndim, int L) {
@@ -468,6 +754,21 @@ static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* 
     for (int l = 0; l < levels; ++l) {
         const wt_level& d = lv[l];
         if (H >= (1 << 30) || W >= (1 << 30)) break;
+        if (l + 1 < levels) {
+            // two levels in one launch: the level-(l+1) approximation never leaves the SM
+            cudaError_t pe = cudaSuccess;
+            if (try_pair<T>(src, batch, (int)H, (int)W, sbs, srs, lv[l], lv[l + 1], L, mode, taps, st, &launches, &pe)) {
+                g_launches.fetch_add(launches, std::memory_order_relaxed);
+                launches = 0;
+                if (pe != cudaSuccess) return cuda_fail(pe, "fwd2d_pair_kernel");
+                const wt_level& d2 = lv[l + 1];
+                src = (const T*)d2.approx; sbs = d2.approx_batch_stride; srs = d2.approx_strides[0];
+                H = d2.dims[0]; W = d2.dims[1];
+                ++l;
+                *first_generic = l + 1;
+                continue;
+            }
+        }
         if (d.strides[1] != 1 || d.approx_strides[1] != 1) break;
         T* out[4];
         int64_t obs[4], ors[4];

@@ -40,6 +40,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 }  // namespace wtb
 #ifndef WTB_NO_FUSED
 #include "fused2d.cuh"
+#include "fused2d_pair.cuh"
 #endif
 namespace wtb {
 
