@@ -109,20 +109,23 @@ def cpu_reference_throughput(sample_batch: int, reps: int):
     """The oracle port (the reference's own torch-CPU operator sequence) on the host cores."""
     from oracle import ptwt_port as P
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(sample_batch, H, W, generator=g, dtype=torch.float32)
-    P.wavedec2(x[:1], WAVELET, mode=MODE, level=LEVEL)  # warm-up (oneDNN primitive creation)
-    best = float("inf")
-    times = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        P.wavedec2(x, WAVELET, mode=MODE, level=LEVEL)
-        dt = time.perf_counter() - t0
-        times.append(dt)
-        best = min(best, dt)
-    return sample_batch * H * W / best / 1e6, cores, times
+    best, best_cores, times = float("inf"), ncpu, []
+    # torch's CPU convolution does not always scale to every hardware thread: give the reference its
+    # best thread count among {all, half (physical cores), 32}
+    for cores in sorted({ncpu, max(ncpu // 2, 1), min(32, ncpu)}, reverse=True):
+        torch.set_num_threads(cores)
+        P.wavedec2(x[:1], WAVELET, mode=MODE, level=LEVEL)  # warm-up (oneDNN primitive creation)
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            P.wavedec2(x, WAVELET, mode=MODE, level=LEVEL)
+            dt = time.perf_counter() - t0
+            times.append(dt)
+            if dt < best:
+                best, best_cores = dt, cores
+    return sample_batch * H * W / best / 1e6, best_cores, times
 
 
 def run_reference(args) -> None:
@@ -133,10 +136,20 @@ def run_reference(args) -> None:
     steps, warmup = max(args.steps, 1), args.warmup
     from oracle import ptwt_port as P
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(sample, H, W, generator=g, dtype=torch.float32)
+    # pick the thread count the reference's operators run fastest with (see cpu_reference_throughput)
+    cores, best = ncpu, float("inf")
+    for cand in sorted({ncpu, max(ncpu // 2, 1), min(32, ncpu)}, reverse=True):
+        torch.set_num_threads(cand)
+        P.wavedec2(x[:1], WAVELET, mode=MODE, level=LEVEL)
+        t0 = time.perf_counter()
+        P.wavedec2(x, WAVELET, mode=MODE, level=LEVEL)
+        dt = time.perf_counter() - t0
+        if dt < best:
+            best, cores = dt, cand
+    torch.set_num_threads(cores)
     for _ in range(max(warmup, 1)):
         P.wavedec2(x, WAVELET, mode=MODE, level=LEVEL)
     t0 = time.perf_counter()
@@ -161,7 +174,7 @@ def run_reference(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step (BASELINE config: 64)")
@@ -244,11 +257,36 @@ def main() -> None:
         max_err = max(float((a[:1].cpu() - b).abs().max()) for a, b in zip(flat_g, flat_w)) / scale
     del out
 
-    # roofline of the transform (dominant kernel = the whole forward pass of the step for now)
+    # roofline: the dominant kernel is the level-1 launch of fwd2d_strip_f32_kernel (72 % of the step);
+    # it is timed alone with CUDA events (a level=1 transform is exactly that one launch), achieved =
+    # its algorithmic bytes 4*(H*W + 4*Mh*Mw) per image / its average duration.  The whole step
+    # (4 launches, approximation bands re-read between levels) is reported as step_*.
     peak, peak_src = measured_peak_gbs()
     alg = algorithmic_bytes_per_image() * B
     med_ms = step_ms[len(step_ms) // 2]
-    achieved = alg / (med_ms * 1e-3) / 1e9
+    step_achieved = alg / (med_ms * 1e-3) / 1e9
+    m1 = coeff_sizes(H, 8, 1)[0]
+    alg_k = 4 * (H * W + 4 * m1 * m1) * B
+    for _ in range(3):
+        wt.wavedec2(x, WAVELET, mode=MODE, level=1)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize(dev)
+    _native.launch_count_reset()
+    k0.record()
+    for _ in range(20):
+        wt.wavedec2(x, WAVELET, mode=MODE, level=1)
+    k1.record()
+    torch.cuda.synchronize(dev)
+    k_launches = _native.launch_count()
+    k_ms = k0.elapsed_time(k1) / 20
+    achieved = alg_k / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get("dominant_kernel_dram_bytes_per_launch")
+        except Exception:  # noqa: BLE001
+            traffic = None
 
     # end to end through the public API with HOST (pinned) buffers: H2D + transform + D2H every step
     e2e = None
@@ -289,7 +327,11 @@ def main() -> None:
                        "l2": "inputs (4.29 GB) and outputs (4.32 GB) exceed the 126 MB L2; no flush needed",
                        "parallelism": f"batch-sharded x{world}, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "fwd2d_strip_f32_kernel<8,64,TMA> (level-1 launch)",
+                         "kernel_algorithmic_bytes_per_launch": alg_k, "kernel_ms_per_launch": k_ms,
+                         "kernel_launches_timed": int(k_launches),
+                         "step_achieved": step_achieved, "step_frac": step_achieved / peak,
                          "algorithmic_bytes_per_step": alg, "median_step_ms": med_ms, "min_step_ms": step_ms[0]},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "parity": {"max_rel_err_vs_oracle": max_err, "tolerance": 1e-5},

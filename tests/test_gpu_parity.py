@@ -331,3 +331,41 @@ def test_requires_grad_is_rejected_loudly():
         wt.wavedec(x, "haar", level=1)
     with torch.no_grad():
         wt.wavedec(x, "haar", level=1)
+
+
+def test_host_pipeline_equals_device_path(monkeypatch):
+    """CPU tensors large enough for the chunked H2D / transform / D2H pipeline give exactly what the
+    device path gives (chunk size forced down so that several chunks and a ragged tail occur)."""
+    from pytorch_wavelet_toolbox_b200 import fwt as F
+
+    monkeypatch.setattr(F, "HOST_PIPELINE_MIN_BYTES", 1)
+    monkeypatch.setattr(F, "HOST_PIPELINE_CHUNK_BYTES", 3 * 96 * 100 * 4)
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(11, 96, 100, generator=g)
+    host = wt.wavedec2(x, "db4", level=2)
+    dev = wt.wavedec2(x.to(DEV), "db4", level=2)
+    for a, b in zip(flatten_coeffs(host), flatten_coeffs(dev)):
+        assert a.device.type == "cpu" and torch.equal(a, b.cpu())
+    x1 = torch.randn(9, 4, 300, generator=g, dtype=torch.float64)
+    h1 = wt.wavedec(x1, "db3", level=3, mode="symmetric")
+    d1 = wt.wavedec(x1.to(DEV), "db3", level=3, mode="symmetric")
+    for a, b in zip(h1, d1):
+        assert torch.equal(a, b.cpu())
+
+
+def test_pair_kernel_when_enabled(monkeypatch):
+    """The experimental two-level fused kernel (WTB200_ENABLE_PAIR=1) must agree with the oracle."""
+    import os
+
+    monkeypatch.setenv("WTB200_ENABLE_PAIR", "1")
+    g = torch.Generator().manual_seed(22)
+    try:
+        for mode in ("zero", "constant", "reflect", "symmetric"):
+            for shape in ((300, 200), (129, 517), (64, 64)):
+                x = torch.randn((2,) + shape, generator=g)
+                _cmp_tree(wt.wavedec2(x.to(DEV), "db4", mode=mode, level=4 if min(shape) > 100 else 2),
+                          P.wavedec2(x, "db4", mode=mode, level=4 if min(shape) > 100 else 2), f"pair {mode} {shape}")
+                _cmp_tree(wt.wavedec2(x.to(DEV), "db2", mode=mode, level=3), P.wavedec2(x, "db2", mode=mode, level=3),
+                          f"pair db2 {mode} {shape}")
+    finally:
+        os.environ.pop("WTB200_ENABLE_PAIR", None)
