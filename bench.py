@@ -288,6 +288,25 @@ def main() -> None:
         except Exception:  # noqa: BLE001
             traffic = None
 
+    # inverse transform of the same coefficients (reported separately)
+    inverse = None
+    if rank == 0 or True:
+        coeffs = step()
+        for _ in range(3):
+            rec = wt.waverec2(coeffs, WAVELET)
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        i0.record()
+        for _ in range(10):
+            rec = wt.waverec2(coeffs, WAVELET)
+        i1.record()
+        torch.cuda.synchronize(dev)
+        inv_ms = i0.elapsed_time(i1) / 10
+        rt_err = float((rec[:2] - x[:2]).abs().max())
+        inverse = {"ms_per_step": inv_ms, "value": B * H * W / (inv_ms * 1e-3) / 1e6, "unit": "Msamples/s (per GPU)",
+                   "step_frac": alg / (inv_ms * 1e-3) / 1e9 / peak, "round_trip_max_abs_err": rt_err}
+        del coeffs, rec
+
     # end to end through the public API with HOST (pinned) buffers: H2D + transform + D2H every step
     e2e = None
     if not args.no_e2e:
@@ -333,7 +352,7 @@ def main() -> None:
                          "kernel_launches_timed": int(k_launches),
                          "step_achieved": step_achieved, "step_frac": step_achieved / peak,
                          "algorithmic_bytes_per_step": alg, "median_step_ms": med_ms, "min_step_ms": step_ms[0]},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "inverse": inverse, "gpu_launches": int(launches), "clocks": clocks,
             "parity": {"max_rel_err_vs_oracle": max_err, "tolerance": 1e-5},
         }
         print(json.dumps(line))

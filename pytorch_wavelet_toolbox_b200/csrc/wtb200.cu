@@ -41,6 +41,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 #ifndef WTB_NO_FUSED
 #include "fused2d.cuh"
 #include "fused2d_pair.cuh"
+#include "inv2d.cuh"
 #endif
 namespace wtb {
 
@@ -402,6 +403,15 @@ static int dwt_inv_t(int ndim, int levels, int L, const double* rlo, const doubl
         }
         if (!lv[l].details || !lv[l].approx) return fail(WT_EINVAL, "level %d: NULL buffer", l + 1);
     }
+#ifndef WTB_NO_FUSED
+    if constexpr (sizeof(T) == 4) {
+        if (fused2d_inv_covers(ndim, 4, L)) {
+            int done = 0;
+            int rc = fused2d_inv_try(levels, L, rlo, rhi, (float*)y, batch, out_dims, ys, ybs, lv, st, &done);
+            if (rc != 0 || done) return rc;
+        }
+    }
+#endif
     int64_t s1, s2;
     generic_scratch_elems(ndim, L, batch, out_dims, 1, &s1, &s2);
     if (ndim > 1 && levels > 0 && ((size_t)(s1 + s2) * sizeof(T) > ws_bytes || !ws))
@@ -539,6 +549,7 @@ size_t wt_dwt_workspace_bytes(int ndim, int dtype, int levels, int filt_len, int
         // general path's requirement only when the fused path is disabled
         return 0;
     }
+    if (inverse && fused2d_inv_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len)) return 0;
 #endif
     int64_t s1, s2;
     generic_scratch_elems(ndim, filt_len, batch, dims, inverse, &s1, &s2);
