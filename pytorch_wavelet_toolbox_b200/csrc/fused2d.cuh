@@ -736,6 +736,27 @@ static bool fused2d_fwd_covers(int ndim, int L) {
 
 // Try the fused path for the first levels of a 2-D analysis; *first_generic receives the number
 // of levels done here (the general path continues from there).
+// One auxiliary stream per device: the batch is cut into chunks that alternate between the caller's
+// stream and this one, so that the small, latency-bound launches of the deep levels of one chunk run
+// under the bandwidth-bound level-1 launch of the next (fork / join with events; no host sync).
+struct AuxStream {
+    cudaStream_t s = nullptr;
+};
+static cudaStream_t aux_stream_for_current_device() {
+    static std::mutex mu;
+    static AuxStream aux[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> g(mu);
+    if (!aux[dev].s && cudaStreamCreateWithFlags(&aux[dev].s, cudaStreamNonBlocking) != cudaSuccess) aux[dev].s = nullptr;
+    return aux[dev].s;
+}
+
+template <typename T>
+static int fused2d_fwd_run(int ndim, int mode, int levels, int L, const double* dlo, const double* dhi, const T* x,
+                           int64_t batch, const int64_t* dims, const int64_t* xs, int64_t xbs, const wt_level* lv,
+                           cudaStream_t st, int* first_generic);
+
 template <typename T>
 static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* dlo, const double* dhi, const T* x,
                            int64_t batch, const int64_t* dims, const int64_t* xs, int64_t xbs, const wt_level* lv,
@@ -743,6 +764,48 @@ static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* 
     *first_generic = 0;
     if (!fused2d_fwd_covers(ndim, L)) return 0;
     if (xs[1] != 1) return 0;
+    int nsplit = 1;
+    if (const char* ev = getenv("WTB200_SPLIT")) nsplit = atoi(ev);
+    else if (levels >= 2 && batch >= 16 && (int64_t)batch * dims[0] * dims[1] >= (int64_t(1) << 27)) nsplit = 2;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (nsplit > 1 && (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) nsplit = 1;
+    cudaStream_t s2 = nsplit > 1 ? aux_stream_for_current_device() : nullptr;
+    if (nsplit <= 1 || !s2 || levels > 32)
+        return fused2d_fwd_run<T>(ndim, mode, levels, L, dlo, dhi, x, batch, dims, xs, xbs, lv, st, first_generic);
+    if (nsplit > batch) nsplit = (int)batch;
+    cudaEvent_t fork, join;
+    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return cuda_fail(cudaGetLastError(), "event");
+    if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) { cudaEventDestroy(fork); return cuda_fail(cudaGetLastError(), "event"); }
+    cudaEventRecord(fork, st);
+    cudaStreamWaitEvent(s2, fork, 0);
+    int rc = 0, fg = levels;
+    wt_level sub[32];
+    for (int c = 0; c < nsplit && rc == 0; ++c) {
+        const int64_t b0 = batch * c / nsplit, b1 = batch * (c + 1) / nsplit;
+        if (b1 <= b0) continue;
+        for (int l = 0; l < levels; ++l) {
+            sub[l] = lv[l];
+            sub[l].details = (T*)lv[l].details + b0 * lv[l].details_batch_stride;
+            sub[l].approx = (T*)lv[l].approx + b0 * lv[l].approx_batch_stride;
+        }
+        int fgc = 0;
+        rc = fused2d_fwd_run<T>(ndim, mode, levels, L, dlo, dhi, x + b0 * xbs, b1 - b0, dims, xs, xbs, sub,
+                                (c & 1) ? s2 : st, &fgc);
+        if (fgc < fg) fg = fgc;
+    }
+    cudaEventRecord(join, s2);
+    cudaStreamWaitEvent(st, join, 0);
+    cudaEventDestroy(fork);
+    cudaEventDestroy(join);
+    *first_generic = fg;
+    return rc;
+}
+
+template <typename T>
+static int fused2d_fwd_run(int ndim, int mode, int levels, int L, const double* dlo, const double* dhi, const T* x,
+                           int64_t batch, const int64_t* dims, const int64_t* xs, int64_t xbs, const wt_level* lv,
+                           cudaStream_t st, int* first_generic) {
+    *first_generic = 0;
     Taps<T> taps;
     for (int k = 0; k < L; ++k) { taps.lo[k] = (T)dlo[k]; taps.hi[k] = (T)dhi[k]; }
     const T* src = x;
