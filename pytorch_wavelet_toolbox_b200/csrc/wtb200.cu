@@ -42,6 +42,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 #include "fused2d.cuh"
 #include "fused2d_pair.cuh"
 #include "inv2d.cuh"
+#include "fwd3d.cuh"
 #endif
 namespace wtb {
 
@@ -371,6 +372,13 @@ static int dwt_fwd_t(int ndim, int mode, int levels, int L, const double* dlo, c
     generic_scratch_elems(ndim, L, batch, dims, 0, &s1, &s2);
     int first_generic = 0;
 #ifndef WTB_NO_FUSED
+    if constexpr (sizeof(T) == 4) {
+        if (fused3d_fwd_covers(ndim, 4, L)) {
+            int done = 0;
+            int rc = fused3d_fwd_try(mode, levels, L, dlo, dhi, (const float*)x, batch, dims, xs, xbs, lv, st, &done);
+            if (rc != 0 || done) return rc;
+        }
+    }
     {
         int rc = fused2d_fwd_try<T>(ndim, mode, levels, L, dlo, dhi, (const T*)x, batch, dims, xs, xbs, lv,
                                     st, &first_generic);
@@ -550,6 +558,7 @@ size_t wt_dwt_workspace_bytes(int ndim, int dtype, int levels, int filt_len, int
         return 0;
     }
     if (inverse && fused2d_inv_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len)) return 0;
+    if (!inverse && fused3d_fwd_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len) && batch <= 65535) return 0;
 #endif
     int64_t s1, s2;
     generic_scratch_elems(ndim, filt_len, batch, dims, inverse, &s1, &s2);
