@@ -147,7 +147,11 @@ int wt_dwt_inv(int ndim, int dtype, int levels, int filt_len,
  *               [nb x w_left], lo_right [nb x w_right], hi_left, hi_right (row-major).
  * x is [batch, n0] contiguous rows (n0 = n[0] - padded[0]).  hi_out[l] receives the detail
  * of level l ([batch, n[l]/2], row stride hi_stride[l]); lo_out the coarsest approximation.
- * scratch must hold 2 * batch * (n[0]/2) elements. */
+ * scratch must hold 2 * batch * (n[0]/2) elements.
+ * allow_fused: non-zero lets consecutive unpadded levels run in one kernel that keeps the approximation
+ * in shared memory; that kernel cannot reach the cross-corner entries of the boundary rows (a top row's
+ * entries in the right window and vice versa), so the caller sets it only when those entries are
+ * negligible (the Python layer: <= 1e-13, true for float64 operators). */
 int wt_matrix_fwd(int dtype, int levels, int filt_len,
                   const double* dec_lo, const double* dec_hi,
                   const int64_t* n, const int32_t* padded, int odd_mode,
@@ -156,7 +160,7 @@ int wt_matrix_fwd(int dtype, int levels, int filt_len,
                   const void* x, int64_t batch, int64_t x_stride,
                   void* const* hi_out, const int64_t* hi_stride,
                   void* lo_out, int64_t lo_stride,
-                  void* scratch, size_t scratch_bytes, void* stream);
+                  void* scratch, size_t scratch_bytes, int allow_fused, void* stream);
 
 /* MatrixWaverec: the mirror image.  Taps are the FLIPPED reconstruction filters'
  * source, i.e. pass rec_lo / rec_hi un-flipped (reference flips them itself,

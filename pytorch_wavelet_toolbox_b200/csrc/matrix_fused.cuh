@@ -1,0 +1,270 @@
+// matrix_fused.cuh -- several levels of the boundary-filter matrix FWT in ONE kernel.
+//
+// The reference applies one sparse operator per level (torch.sparse.mm, src/ptwt/matmul_transform.py:
+// 409-425), so every approximation vector makes a round trip through memory: 2x the compulsory traffic
+// for a 12-level transform.  Here a CTA takes a chunk of the signal through up to MAXK levels in shared
+// memory: only the detail coefficients and the last approximation leave the SM.
+//
+//   * a CTA owns TK outputs of the last fused level and, going backwards, the sample ranges of the
+//     finer levels they depend on (halo L/2 - 1 left, L/2 right per level);
+//   * samples are kept de-interleaved (even / odd polyphase arrays): output i reads samples
+//     2i - (L/2-1) .. 2i + L/2, i.e. CONTIGUOUS runs of both arrays, so that two adjacent outputs per
+//     thread need a handful of conflict-free 128-bit shared loads;
+//   * the orthogonalised boundary rows (dense blocks) are evaluated by the CTAs at the two ends; the
+//     round-off sized cross-corner entries the QR leaves behind are not reachable from a chunk, so the
+//     host only selects this kernel when they are below 1e-13 (float64) -- otherwise the per-level
+//     kernels, which keep them, run instead.
+#pragma once
+
+#include "common.cuh"
+
+namespace wtb {
+
+constexpr int MATF_MAXK = 6;
+
+template <typename T>
+struct MatFusedParams {
+    const T* x;                  // [batch, n0]
+    int64_t x_stride;
+    T* hi[MATF_MAXK];            // detail of fused level j (0-based), [batch, n_j / 2]
+    int64_t hi_stride[MATF_MAXK];
+    T* lo;                       // approximation of the last fused level
+    int64_t lo_stride;
+    int k;                       // fused levels
+    int n[MATF_MAXK + 1];        // n[0] = input length, n[j] = n[j-1] / 2
+    int nb_top[MATF_MAXK], nb_bot[MATF_MAXK], w_left[MATF_MAXK], w_right[MATF_MAXK];
+    const T* lo_left[MATF_MAXK];
+    const T* lo_right[MATF_MAXK];
+    const T* hi_left[MATF_MAXK];
+    const T* hi_right[MATF_MAXK];
+    int tk;                      // outputs of the last fused level per CTA
+    int cap0;                    // capacity (samples) of the level-0 staging arrays
+    T flo[16], fhi[16];          // taps in window order: out[i] = sum_k f[k] a[2i - (L/2-1) + k]
+};
+
+template <typename T> struct Vec2Of;
+template <> struct Vec2Of<double> { using type = double2; };
+template <> struct Vec2Of<float> { using type = float2; };
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256) mat_fwd_fused_kernel(const __grid_constant__ MatFusedParams<T> p) {
+    using V2 = typename Vec2Of<T>::type;
+    constexpr int HL = L / 2 - 1, HR = L / 2;
+    constexpr int DELTA = HL & 1;                 // parity of the first sample of an even output's window
+    constexpr int PQ = ((HL + 1) / 2) & 1;        // parity of the first polyphase index (ranges start at multiples of 4)
+    constexpr int NE = (L + 2 + DELTA + 1) / 2;   // polyphase entries covering the window of an output pair
+    constexpr int NEV = (NE + PQ + 1) / 2 * 2;    // rounded to whole 2-element vectors
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* bufA = reinterpret_cast<T*>(smem_raw);     // even | odd arrays of the current level input
+    const int capA = p.cap0 / 2 + 8;              // entries per polyphase array (level 0)
+    T* bufB = bufA + 2 * capA;                    // even | odd arrays of the next level
+
+    const int tid = threadIdx.x;
+    const int b = blockIdx.y;
+    const int K = p.k;
+
+    // ranges: rlo[j], rhi[j] = level-j indices this CTA computes (j >= 1) / stages (j = 0)
+    int rlo[MATF_MAXK + 1], rhi[MATF_MAXK + 1];
+    rlo[K] = blockIdx.x * p.tk;
+    rhi[K] = min(rlo[K] + p.tk, p.n[K]);
+    if (rlo[K] >= p.n[K]) return;
+#pragma unroll
+    for (int j = MATF_MAXK; j >= 1; --j) {
+        if (j > K) continue;
+        const int half = p.n[j];                  // outputs of level j
+        int lo = 2 * rlo[j] - HL, hi = 2 * (rhi[j] - 1) + HR + 1;
+        if (rlo[j] < p.nb_top[j - 1]) lo = 0, hi = max(hi, p.w_left[j - 1]);
+        if (rhi[j] > half - p.nb_bot[j - 1]) hi = p.n[j - 1], lo = min(lo, p.n[j - 1] - p.w_right[j - 1]);
+        lo = max(lo, 0) & ~3;                     // multiple of 4: polyphase index starts even
+        hi = min(hi, p.n[j - 1]);
+        rlo[j - 1] = lo;
+        rhi[j - 1] = hi;
+        if (j - 1 >= 1) {
+            // the computed range of level j-1 must start on an even output and stay inside its own extent
+            rlo[j - 1] = lo;
+        }
+    }
+
+    // stage the level-0 samples, de-interleaved
+    {
+        const T* __restrict__ xb = p.x + (int64_t)b * p.x_stride;
+        const int s0 = rlo[0], cnt = rhi[0] - rlo[0];
+        T* ev = bufA;
+        T* od = bufA + capA;
+        for (int q = tid; 2 * q < cnt; q += 256) {
+            const int s = s0 + 2 * q;
+            if (s + 1 < rhi[0]) {
+                const V2 v = __ldg(reinterpret_cast<const V2*>(xb + s));   // s is even and the row start is aligned
+                ev[q] = v.x; od[q] = v.y;
+            } else {
+                ev[q] = __ldg(xb + s); od[q] = T(0);
+            }
+        }
+    }
+    __syncthreads();
+
+    T* cur = bufA;
+    int cur_cap = capA;
+    T* nxt = bufB;
+#pragma unroll 1
+    for (int j = 1; j <= K; ++j) {
+        const int half = p.n[j];
+        const int nprev = p.n[j - 1];
+        const int in0 = rlo[j - 1];               // sample index of polyphase entry 0
+        const int nxt_cap = ((rhi[j] - rlo[j]) / 2 + 9) & ~1;   // even: the odd array stays 16-byte aligned
+        const T* ev = cur;
+        const T* od = cur + cur_cap;
+        T* nev = nxt;
+        T* nod = nxt + nxt_cap;
+        const int own0 = (blockIdx.x * p.tk) << (K - j), own1 = min(((blockIdx.x + 1) * p.tk) << (K - j), half);
+        T* __restrict__ hib = p.hi[j - 1] + (int64_t)b * p.hi_stride[j - 1];
+        T* __restrict__ lob = p.lo + (int64_t)b * p.lo_stride;
+        const int nbt = p.nb_top[j - 1], nbb = p.nb_bot[j - 1];
+        const int npairs = (rhi[j] - rlo[j] + 1) / 2;
+        for (int pr = tid; pr < npairs; pr += 256) {
+            const int i = rlo[j] + 2 * pr;        // even output index
+            T alo[2] = {T(0), T(0)}, ahi[2] = {T(0), T(0)};
+            const int q0 = ((2 * i - HL - in0) >> 1) - PQ;           // even polyphase index of the first load
+            const bool interior = (i >= nbt) && (i + 1 < half - nbb) && (q0 >= 0);
+            if (interior) {
+                // window of the pair: samples 2i - HL .. 2i + 2 + HR
+                T e[NEV], o[NEV];
+#pragma unroll
+                for (int v = 0; v < NEV / 2; ++v) {
+                    const V2 a = *reinterpret_cast<const V2*>(ev + q0 + 2 * v);
+                    const V2 c = *reinterpret_cast<const V2*>(od + q0 + 2 * v);
+                    e[2 * v] = a.x; e[2 * v + 1] = a.y; o[2 * v] = c.x; o[2 * v + 1] = c.y;
+                }
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+#pragma unroll
+                    for (int k = 0; k < L; ++k) {
+                        const int d = 2 * r + k + DELTA + 2 * PQ;    // offset from sample in0 + 2 q0
+                        const T s = (d & 1) ? o[d >> 1] : e[d >> 1];
+                        alo[r] = fma(p.flo[k], s, alo[r]);
+                        ahi[r] = fma(p.fhi[k], s, ahi[r]);
+                    }
+                }
+            } else {
+                for (int r = 0; r < 2; ++r) {
+                    const int ii = i + r;
+                    if (ii >= half) continue;
+                    auto sample = [&](int s) -> T {
+                        const int d = s - in0;
+                        return (d & 1) ? od[d >> 1] : ev[d >> 1];
+                    };
+                    if (ii < nbt || ii >= half - nbb) {
+                        const int rr = ii < nbt ? ii : nbt + (ii - (half - nbb));
+                        const bool top = ii < nbt;
+                        // dense boundary row: all block loads are issued up front (fixed trip count)
+                        const int w = top ? p.w_left[j - 1] : p.w_right[j - 1];
+                        const int s0 = top ? 0 : nprev - w;
+                        const T* __restrict__ bl_ = (top ? p.lo_left[j - 1] : p.lo_right[j - 1]) + rr * w;
+                        const T* __restrict__ bh_ = (top ? p.hi_left[j - 1] : p.hi_right[j - 1]) + rr * w;
+                        T cl[16], ch[16];
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            cl[c] = c < w ? __ldg(bl_ + c) : T(0);
+                            ch[c] = c < w ? __ldg(bh_ + c) : T(0);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            if (c < w) {
+                                const T sv = sample(s0 + c);
+                                alo[r] = fma(cl[c], sv, alo[r]);
+                                ahi[r] = fma(ch[c], sv, ahi[r]);
+                            }
+                        }
+                        for (int c = 16; c < w; ++c) {   // wider blocks than any orthogonal wavelet <= 16 taps produces
+                            const T sv = sample(s0 + c);
+                            alo[r] = fma(__ldg(bl_ + c), sv, alo[r]);
+                            ahi[r] = fma(__ldg(bh_ + c), sv, ahi[r]);
+                        }
+                    } else {
+                        for (int k = 0; k < L; ++k) {
+                            const int s = 2 * ii - HL + k;
+                            if (s < 0 || s >= nprev) continue;
+                            const T v = sample(s);
+                            alo[r] = fma(p.flo[k], v, alo[r]);
+                            ahi[r] = fma(p.fhi[k], v, ahi[r]);
+                        }
+                    }
+                }
+            }
+            // approximation -> next level (de-interleaved), detail -> HBM (owned range only)
+            const int rel = (i - rlo[j]) >> 1;
+            if (j < K) { nev[rel] = alo[0]; nod[rel] = alo[1]; }
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int ii = i + r;
+                if (ii >= own0 && ii < own1) {
+                    hib[ii] = ahi[r];
+                    if (j == K) lob[ii] = alo[r];
+                }
+            }
+        }
+        __syncthreads();
+        T* t = const_cast<T*>(cur); cur = nxt; nxt = t;
+        cur_cap = nxt_cap;
+    }
+}
+
+
+// Host: launch one fused group of k levels (level indices l .. l+k-1 of the caller's arrays).
+template <typename T>
+static bool launch_mat_fwd_fused(int L, int k, const int64_t* n, const int32_t* nbt, const int32_t* nbb, const int32_t* wl,
+                                 const int32_t* wr, const T* const* blk_ptrs /* 4 per level */, const T* x, int64_t xs,
+                                 int64_t batch, void* const* hi_out, const int64_t* hi_stride, T* lo_out, int64_t lo_stride,
+                                 const Taps<T>& taps, cudaStream_t st, cudaError_t* err) {
+    *err = cudaSuccess;
+    if ((L & 1) || L < 2 || L > 16 || k < 2 || k > MATF_MAXK || batch > 65535) return false;
+    if (((uintptr_t)x & 15) || (xs & 1) || n[0] >= (int64_t(1) << 30)) return false;
+    MatFusedParams<T> p;
+    memset(&p, 0, sizeof(p));
+    p.x = x; p.x_stride = xs; p.k = k;
+    p.n[0] = (int)n[0];
+    for (int j = 0; j < k; ++j) {
+        if (n[j] & 1) return false;
+        p.n[j + 1] = (int)(n[j] / 2);
+        if (j + 1 < k && n[j + 1] != n[j] / 2) return false;
+        p.hi[j] = (T*)hi_out[j]; p.hi_stride[j] = hi_stride[j];
+        p.nb_top[j] = nbt[j]; p.nb_bot[j] = nbb[j]; p.w_left[j] = wl[j]; p.w_right[j] = wr[j];
+        p.lo_left[j] = blk_ptrs[4 * j]; p.lo_right[j] = blk_ptrs[4 * j + 1];
+        p.hi_left[j] = blk_ptrs[4 * j + 2]; p.hi_right[j] = blk_ptrs[4 * j + 3];
+        if (nbt[j] + nbb[j] > p.n[j + 1]) return false;
+    }
+    p.lo = lo_out; p.lo_stride = lo_stride;
+    for (int q = 0; q < L; ++q) { p.flo[q] = taps.lo[L - 1 - q]; p.fhi[q] = taps.hi[L - 1 - q]; }
+    const int nk = p.n[k];
+    const int chunk0 = sizeof(T) == 8 ? 4096 : 8192;              // level-0 samples per CTA
+    int tk = chunk0 >> k;
+    if (tk < 4) tk = 4;
+    tk = (tk + 3) & ~3;
+    if (tk > nk) tk = (nk + 3) & ~3;
+    p.tk = tk;
+    int cap0 = (tk << k) + ((L + 6) << k) + 64;
+    if (cap0 > p.n[0] + 16) cap0 = (p.n[0] + 16 + 3) & ~3;
+    cap0 = (cap0 + 3) & ~3;
+    p.cap0 = cap0;
+    const size_t smem = (size_t)(2 * (cap0 / 2 + 8) + 2 * (cap0 / 4 + 16)) * sizeof(T);
+    if (smem > 200 * 1024) return false;
+    dim3 grid((nk + tk - 1) / tk, (unsigned)batch);
+#define WTB_MF(LL)                                                                                              \
+    case LL: {                                                                                                  \
+        cudaError_t e = cudaFuncSetAttribute(mat_fwd_fused_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem);                                                        \
+        if (e != cudaSuccess) { *err = e; return true; }                                                        \
+        mat_fwd_fused_kernel<T, LL><<<grid, 256, smem, st>>>(p);                                                \
+        break;                                                                                                  \
+    }
+    switch (L) {
+        WTB_MF(2) WTB_MF(4) WTB_MF(6) WTB_MF(8) WTB_MF(10) WTB_MF(12) WTB_MF(14) WTB_MF(16)
+        default: return false;
+    }
+#undef WTB_MF
+    *err = cudaGetLastError();
+    return true;
+}
+
+}  // namespace wtb

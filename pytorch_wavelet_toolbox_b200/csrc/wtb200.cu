@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "generic_axis.cuh"
 #include "matrix_generic.cuh"
+#include "axis1d_fast.cuh"
+#include "matrix_fused.cuh"
 #if !defined(WTB_NO_FUSED) && !__has_include("fused2d.cuh")
 #define WTB_NO_FUSED 1
 #endif
@@ -174,7 +176,20 @@ static int dwt_fwd_generic(int ndim, int mode, int levels, int L, const Taps<T>&
             View<const T> xv{src, cbs, 0, cs[0]};
             View<T> lo = band(0), hi = band(1);
             lo.s_n = st_of(0)[0]; hi.s_n = st_of(1)[0];
-            e = launch_axis_fwd<T>(xv, lo, hi, batch, 1, cur[0], 1, mode, L, taps, st);
+            bool done1 = false;
+            if (cs[0] == 1 && lo.s_n == 1 && hi.s_n == 1 && cur[0] < (1 << 30) && L <= 16 && !getenv("WTB200_DISABLE_FUSED")) {
+                Fast1dParams<T> fp;
+                memset(&fp, 0, sizeof(fp));
+                fp.x = src; fp.lo = lo.ptr; fp.hi = hi.ptr;
+                fp.xs = cbs; fp.ls = lo.s_o1; fp.hs = hi.s_o1;
+                fp.n = fp.n_in = (int)cur[0]; fp.m = (int)d.dims[0];
+                fp.base = -pad_left(L); fp.mode = mode;
+                for (int k = 0; k < L; ++k) { fp.flo[k] = taps.lo[L - 1 - k]; fp.fhi[k] = taps.hi[L - 1 - k]; }
+                done1 = launch_axis1d_fast<T, false>(fp, L, batch, st, &e);
+                if (done1) g_launches.fetch_add(1, std::memory_order_relaxed);
+                if (done1 && e != cudaSuccess) return cuda_fail(e, "axis1d_fast_kernel");
+            }
+            if (!done1) e = launch_axis_fwd<T>(xv, lo, hi, batch, 1, cur[0], 1, mode, L, taps, st);
             if (e != cudaSuccess) return cuda_fail(e, "axis_fwd_kernel");
         } else if (ndim == 2) {
             const int64_t H = cur[0], W = cur[1], Mw = d.dims[1];
@@ -276,7 +291,19 @@ static int dwt_inv_generic(int ndim, int levels, int L, const Taps<T>& taps, T* 
             View<const T> lo = band(0), hi = band(1);
             lo.s_n = st_of(0)[0]; hi.s_n = st_of(1)[0];
             View<T> yv{dst, dbs, 0, ds[0]};
-            e = launch_axis_inv<T>(lo, hi, yv, batch, 1, d.dims[0], dd[0], 1, L, taps, st);
+            bool done1 = false;
+            if (lo.s_n == 1 && hi.s_n == 1 && ds[0] == 1 && d.dims[0] < (1 << 29) && L <= 16 && !getenv("WTB200_DISABLE_FUSED")) {
+                Fast1dInvParams<T> fp;
+                memset(&fp, 0, sizeof(fp));
+                fp.lo = lo.ptr; fp.hi = hi.ptr; fp.y = dst;
+                fp.ls = lo.s_o1; fp.hs = hi.s_o1; fp.ys = dbs;
+                fp.m = (int)d.dims[0]; fp.nout = (int)dd[0];
+                for (int k = 0; k < L; ++k) { fp.rlo[k] = taps.lo[k]; fp.rhi[k] = taps.hi[k]; }
+                done1 = launch_axis1d_inv_fast<T>(fp, L, batch, st, &e);
+                if (done1) g_launches.fetch_add(1, std::memory_order_relaxed);
+                if (done1 && e != cudaSuccess) return cuda_fail(e, "axis1d_inv_fast_kernel");
+            }
+            if (!done1) e = launch_axis_inv<T>(lo, hi, yv, batch, 1, d.dims[0], dd[0], 1, L, taps, st);
             if (e != cudaSuccess) return cuda_fail(e, "axis_inv_kernel");
         } else if (ndim == 2) {
             const int64_t Mh = d.dims[0], Mw = d.dims[1], OH = dd[0], OW = dd[1];
@@ -433,7 +460,7 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
                         const int32_t* padded, int odd_mode, const int32_t* nbt, const int32_t* nbb,
                         const int32_t* wt, const int32_t* wb, const void* blocks, const void* x, int64_t batch,
                         int64_t xs, void* const* hi_out, const int64_t* hi_stride, void* lo_out,
-                        int64_t lo_stride, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                        int64_t lo_stride, void* scratch, size_t scratch_bytes, int allow_fused, cudaStream_t st) {
     Taps<T> taps;
     fill_taps(taps, dlo, dhi, L, false);
     const size_t need = levels > 1 ? (size_t)2 * batch * (n[0] / 2) * sizeof(T) : 0;
@@ -442,8 +469,44 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
     const T* src = (const T*)x;
     int64_t src_stride = xs;
     T* ping[2] = {(T*)scratch, (T*)scratch + batch * (n[0] / 2)};
+    // block pointers of every level (lo_left, lo_right, hi_left, hi_right)
+    const T* bptr[4 * 64];
+    if (levels > 64) return fail(WT_EUNSUPPORTED, "more than 64 levels");
+    {
+        const T* q = blk;
+        for (int l = 0; l < levels; ++l) {
+            const int64_t nb = (int64_t)nbt[l] + nbb[l];
+            bptr[4 * l] = q; q += nb * wt[l];
+            bptr[4 * l + 1] = q; q += nb * wb[l];
+            bptr[4 * l + 2] = q; q += nb * wt[l];
+            bptr[4 * l + 3] = q; q += nb * wb[l];
+        }
+    }
     for (int l = 0; l < levels; ++l) {
         if (n[l] < 2 || (n[l] & 1)) return fail(WT_ESHAPE, "level %d: operator size %lld must be even", l + 1, (long long)n[l]);
+        if (allow_fused && !getenv("WTB200_DISABLE_FUSED")) {
+            // group of consecutive unpadded levels -> one fused launch
+            int k = 0;
+            while (l + k < levels && k < MATF_MAXK && !padded[l + k] && !(n[l + k] & 1) &&
+                   (k == 0 || n[l + k] == n[l + k - 1] / 2))
+                ++k;
+            if (k >= 2) {
+                const bool last = (l + k == levels);
+                T* lo_dst = last ? (T*)lo_out : ping[(l + k - 1) & 1];
+                const int64_t lo_ds = last ? lo_stride : n[l + k - 1] / 2;
+                cudaError_t e = cudaSuccess;
+                if (launch_mat_fwd_fused<T>(L, k, n + l, nbt + l, nbb + l, wt + l, wb + l, bptr + 4 * l, src, src_stride, batch,
+                                            hi_out + l, hi_stride + l, lo_dst, lo_ds, taps, st, &e)) {
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                    if (e != cudaSuccess) return cuda_fail(e, "mat_fwd_fused_kernel");
+                    src = lo_dst; src_stride = lo_ds;
+                    // keep blk in step with the per-level path
+                    blk = bptr[4 * (l + k - 1) + 3] + ((int64_t)nbt[l + k - 1] + nbb[l + k - 1]) * wb[l + k - 1];
+                    l += k - 1;
+                    continue;
+                }
+            }
+        }
         MatFwdParams<T> p;
         p.x = src; p.x_stride = src_stride;
         p.batch = batch; p.n = n[l]; p.n_in = n[l] - (padded[l] ? 1 : 0);
@@ -461,9 +524,25 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
         p.taps = taps;
         const int64_t total = batch * (n[l] / 2);
         if (total > 0) {
-            mat_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+            bool done1 = false;
+            cudaError_t e = cudaSuccess;
+            if (n[l] < (1 << 30) && !(L & 1) && L <= 16 && !getenv("WTB200_DISABLE_FUSED")) {
+                Fast1dParams<T> fp;
+                memset(&fp, 0, sizeof(fp));
+                fp.x = p.x; fp.lo = p.lo; fp.hi = p.hi;
+                fp.xs = p.x_stride; fp.ls = p.lo_stride; fp.hs = p.hi_stride;
+                fp.n = (int)p.n; fp.n_in = (int)p.n_in; fp.m = (int)(p.n / 2);
+                fp.base = p.shift - (L - 1); fp.mode = odd_mode;
+                fp.nb_top = p.nb_top; fp.nb_bot = p.nb_bot; fp.w_left = p.w_left; fp.w_right = p.w_right;
+                fp.lo_left = p.lo_left; fp.lo_right = p.lo_right; fp.hi_left = p.hi_left; fp.hi_right = p.hi_right;
+                for (int k = 0; k < L; ++k) { fp.flo[k] = taps.lo[L - 1 - k]; fp.fhi[k] = taps.hi[L - 1 - k]; }
+                done1 = launch_axis1d_fast<T, true>(fp, L, batch, st, &e);
+            }
+            if (!done1) {
+                mat_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+                e = cudaGetLastError();
+            }
             g_launches.fetch_add(1, std::memory_order_relaxed);
-            cudaError_t e = cudaGetLastError();
             if (e != cudaSuccess) return cuda_fail(e, "mat_fwd_kernel");
         }
         src = p.lo; src_stride = p.lo_stride;
@@ -603,7 +682,7 @@ int wt_matrix_fwd(int dtype, int levels, int filt_len, const double* dec_lo, con
                   const int64_t* n, const int32_t* padded, int odd_mode, const int32_t* nb_top,
                   const int32_t* nb_bot, const int32_t* w_left, const int32_t* w_right, const void* blocks,
                   const void* x, int64_t batch, int64_t x_stride, void* const* hi_out, const int64_t* hi_stride,
-                  void* lo_out, int64_t lo_stride, void* scratch, size_t scratch_bytes, void* stream) {
+                  void* lo_out, int64_t lo_stride, void* scratch, size_t scratch_bytes, int allow_fused, void* stream) {
     if (dtype != WT_F32 && dtype != WT_F64) return fail(WT_EINVAL, "dtype must be WT_F32 or WT_F64");
     if (levels < 1) return fail(WT_EINVAL, "levels must be >= 1");
     if (filt_len < 2 || filt_len > WT_MAX_FILT_LEN) return fail(WT_EUNSUPPORTED, "filter length %d", filt_len);
@@ -616,10 +695,10 @@ int wt_matrix_fwd(int dtype, int levels, int filt_len, const double* dec_lo, con
     if (dtype == WT_F32)
         return matrix_fwd_t<float>(levels, filt_len, dec_lo, dec_hi, n, padded, odd_mode, nb_top, nb_bot, w_left,
                                    w_right, blocks, x, batch, x_stride, hi_out, hi_stride, lo_out, lo_stride,
-                                   scratch, scratch_bytes, st);
+                                   scratch, scratch_bytes, allow_fused, st);
     return matrix_fwd_t<double>(levels, filt_len, dec_lo, dec_hi, n, padded, odd_mode, nb_top, nb_bot, w_left,
                                 w_right, blocks, x, batch, x_stride, hi_out, hi_stride, lo_out, lo_stride, scratch,
-                                scratch_bytes, st);
+                                scratch_bytes, allow_fused, st);
 }
 
 int wt_matrix_inv(int dtype, int levels, int filt_len, const double* rec_lo, const double* rec_hi,

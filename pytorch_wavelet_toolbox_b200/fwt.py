@@ -16,6 +16,7 @@ call is a drop-in for CPU callers too; there is no CPU compute path.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 from dataclasses import dataclass, field
 from typing import Any, Optional, Sequence, Union
@@ -111,6 +112,12 @@ def _band_strides(dims: Sequence[int], pitch: int) -> tuple[int, ...]:
 
 
 def _make_plan(in_dims: Sequence[int], filt_len: int, levels: int, itemsize: int) -> _Plan:
+    """Cached: the layout depends only on (extents, filter length, level count, element size)."""
+    return _make_plan_cached(tuple(int(d) for d in in_dims), int(filt_len), int(levels), int(itemsize))
+
+
+@functools.lru_cache(maxsize=512)
+def _make_plan_cached(in_dims: tuple, filt_len: int, levels: int, itemsize: int) -> _Plan:
     ndim = len(in_dims)
     plan = _Plan(ndim, filt_len, tuple(int(d) for d in in_dims))
     row_al = max(ROW_ALIGN_BYTES // itemsize, 1)
@@ -280,13 +287,27 @@ def _fill_levels(plan: _Plan, buf: torch.Tensor, scratch: torch.Tensor):
     return arr
 
 
+@functools.lru_cache(maxsize=256)
+def _taps_c_cached(values: tuple, dt: torch.dtype):
+    arr = taps_in_dtype(list(values), dt)
+    return arr, arr.ctypes.data_as(N._f64p)
+
+
+def _taps_c(seq, dt: torch.dtype):
+    """Filter taps as a ctypes double array (rounded to the compute dtype first); cached for plain
+    Python sequences, rebuilt for tensors (learnable filters)."""
+    if isinstance(seq, torch.Tensor):
+        return N.f64_array(taps_in_dtype(seq, dt))
+    return _taps_c_cached(tuple(float(v) for v in seq), dt)
+
+
 def _run_fwd(xd: torch.Tensor, plan: _Plan, mode: str, dec_lo, dec_hi, buf: torch.Tensor,
              scratch: torch.Tensor) -> None:
     lib = N.load()
     dt = xd.dtype
     batch = xd.shape[0]
-    lo_arr, lo_p = N.f64_array(taps_in_dtype(dec_lo, dt))
-    hi_arr, hi_p = N.f64_array(taps_in_dtype(dec_hi, dt))
+    lo_arr, lo_p = _taps_c(dec_lo, dt)
+    hi_arr, hi_p = _taps_c(dec_hi, dt)
     dims_arr, dims_p = N.i64_array(plan.in_dims)
     xs_arr, xs_p = N.i64_array(xd.stride()[1:])
     levels = _fill_levels(plan, buf, scratch)
@@ -447,8 +468,8 @@ def _synthesis(approx: torch.Tensor, levels_in: list[list[torch.Tensor]], probes
         out_dims = out_dims_per_level[-1]
         y = torch.empty((batch,) + out_dims, dtype=dt, device=dev)
         lib = N.load()
-        lo_arr, lo_p = N.f64_array(taps_in_dtype(rec_lo, dt))
-        hi_arr, hi_p = N.f64_array(taps_in_dtype(rec_hi, dt))
+        lo_arr, lo_p = _taps_c(rec_lo, dt)
+        hi_arr, hi_p = _taps_c(rec_hi, dt)
         od_arr, od_p = N.i64_array(out_dims)
         ys_arr, ys_p = N.i64_array(y.stride()[1:])
         code = _dtype_code(dt)

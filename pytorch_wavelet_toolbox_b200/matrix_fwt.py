@@ -164,6 +164,22 @@ def _level_blocks_cached(lo_key: bytes, hi_key: bytes, dtype_name: str, n: int, 
     return blk
 
 
+#: the multi-level fused kernel cannot reach a boundary row's entries in the opposite corner window;
+#: it is used only when all of them are at most this large (round-off of the float64 QR: ~1e-16)
+FUSED_CROSS_CORNER_MAX = 1e-13
+
+
+def _cross_corner_max(blocks: Sequence["_LevelBlocks"]) -> float:
+    worst = 0.0
+    for b in blocks:
+        nt = b.nb_top
+        for top_part, bot_part in ((b.lo_right[:nt], b.lo_left[nt:]), (b.hi_right[:nt], b.hi_left[nt:])):
+            for t in (top_part, bot_part):
+                if t.numel():
+                    worst = max(worst, float(t.abs().max()))
+    return worst
+
+
 def _level_blocks(lo_taps: np.ndarray, hi_taps: np.ndarray, dtype: torch.dtype, n: int, method: str) -> _LevelBlocks:
     return _level_blocks_cached(lo_taps.tobytes(), hi_taps.tobytes(), str(dtype).split(".")[-1], int(n), method)
 
@@ -424,7 +440,8 @@ class MatrixWavedec:
                 N.MODES[self.odd_coeff_padding_mode if (self.padded or first_pad) else "zero"],
                 nbt_p, nbb_p, wt_p, wb_p, flat.data_ptr(), xd.data_ptr(), batch, xd.stride(0),
                 hi_ptrs, hi_strides, out.data_ptr(), out.stride(0),
-                scratch.data_ptr(), scratch_elems * es, torch.cuda.current_stream(dev).cuda_stream,
+                scratch.data_ptr(), scratch_elems * es, 1 if _cross_corner_max(blocks) <= FUSED_CROSS_CORNER_MAX else 0,
+                torch.cuda.current_stream(dev).cuda_stream,
             )
             N.check(rc, "wt_matrix_fwd")
             if on_host:
