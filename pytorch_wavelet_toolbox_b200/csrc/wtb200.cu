@@ -45,6 +45,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 #include "fused2d_pair.cuh"
 #include "inv2d.cuh"
 #include "fwd3d.cuh"
+#include "inv3d.cuh"
 #endif
 namespace wtb {
 
@@ -445,6 +446,11 @@ static int dwt_inv_t(int ndim, int levels, int L, const double* rlo, const doubl
             int rc = fused2d_inv_try(levels, L, rlo, rhi, (float*)y, batch, out_dims, ys, ybs, lv, st, &done);
             if (rc != 0 || done) return rc;
         }
+        if (fused3d_inv_covers(ndim, 4, L)) {
+            int done = 0;
+            int rc = fused3d_inv_try(levels, L, rlo, rhi, (float*)y, batch, out_dims, ys, ybs, lv, st, &done);
+            if (rc != 0 || done) return rc;
+        }
     }
 #endif
     int64_t s1, s2;
@@ -638,6 +644,7 @@ size_t wt_dwt_workspace_bytes(int ndim, int dtype, int levels, int filt_len, int
     }
     if (inverse && fused2d_inv_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len)) return 0;
     if (!inverse && fused3d_fwd_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len) && batch <= 65535) return 0;
+    if (inverse && fused3d_inv_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len) && batch <= 65535) return 0;
 #endif
     int64_t s1, s2;
     generic_scratch_elems(ndim, filt_len, batch, dims, inverse, &s1, &s2);
