@@ -23,14 +23,17 @@ from .constants import (
 )
 from .fwt import wavedec, wavedec2, wavedec3, waverec, waverec2, waverec3
 from .matrix_fwt import MatrixWavedec, MatrixWaverec, construct_boundary_a, construct_boundary_s
+from .separable import fswavedec2, fswavedec3, fswaverec2, fswaverec3
 
 __version__ = "0.1.0"
 
 HOT_PATH_NAMES = (
     "wavedec", "waverec", "wavedec2", "waverec2", "wavedec3", "waverec3", "MatrixWavedec", "MatrixWaverec",
 )
+#: "next" rows of SURVEY.md section 8(f) that ride on the same kernels
+NEXT_ROW_NAMES = ("fswavedec2", "fswavedec3", "fswaverec2", "fswaverec3")
 
-__all__ = list(HOT_PATH_NAMES) + [
+__all__ = list(HOT_PATH_NAMES) + list(NEXT_ROW_NAMES) + [
     "Wavelet", "WaveletTensorTuple", "WaveletDetailTuple2d", "WaveletDetailDict", "WaveletCoeff1d",
     "WaveletCoeff2d", "WaveletCoeffNd", "construct_boundary_a", "construct_boundary_s", "install", "uninstall",
 ]
@@ -50,7 +53,7 @@ def install() -> list[str]:
     import sys
 
     ptwt = importlib.import_module("ptwt")
-    mine = {name: globals()[name] for name in HOT_PATH_NAMES}
+    mine = {name: globals()[name] for name in HOT_PATH_NAMES + NEXT_ROW_NAMES}
     replaced = []
     for modname, mod in list(sys.modules.items()):
         if mod is None or not (modname == "ptwt" or modname.startswith("ptwt.")):

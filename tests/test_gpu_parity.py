@@ -369,3 +369,31 @@ def test_pair_kernel_when_enabled(monkeypatch):
                           f"pair db2 {mode} {shape}")
     finally:
         os.environ.pop("WTB200_ENABLE_PAIR", None)
+
+
+def test_separable_front_ends():
+    """fswavedec2/3 + fswaverec2/3: dict containers over the fused kernels."""
+    g = torch.Generator().manual_seed(23)
+    x = torch.randn(2, 45, 52, generator=g, dtype=torch.float64)
+    for mode in ("zero", "reflect", "periodic"):
+        fs = wt.fswavedec2(x.to(DEV), "db3", mode=mode, level=2)
+        wd = P.wavedec2(x, "db3", mode=mode, level=2)
+        assert list(fs[1].keys()) == ["da", "ad", "dd"]
+        assert_close_rel(fs[0], wd[0], scale=10.0, what="fs approx")
+        for d, t in zip(fs[1:], wd[1:]):
+            assert_close_rel(d["da"], t.horizontal, scale=10.0, what="da")
+            assert_close_rel(d["ad"], t.vertical, scale=10.0, what="ad")
+            assert_close_rel(d["dd"], t.diagonal, scale=10.0, what="dd")
+        rec = wt.fswaverec2(fs, "db3")
+        assert_close_rel(rec[..., :45, :52], x, scale=10.0, what="fs round trip")
+    x3 = torch.randn(2, 20, 22, 24, generator=g)
+    fs = wt.fswavedec3(x3.to(DEV), "haar", level=2)
+    wd = P.wavedec3(x3, "haar", mode="reflect", level=2)
+    assert list(fs[1].keys()) == ["daa", "ada", "dda", "aad", "dad", "add", "ddd"]
+    for d, t in zip(fs[1:], wd[1:]):
+        for k in d:
+            assert_close_rel(d[k], t[k], scale=10.0, what=k)
+    assert_close_rel(wt.fswaverec3(fs, "haar"), x3, scale=10.0, what="fs3 round trip")
+    assert wt.fswavedec2(x.to(DEV), "db3")[0].shape[-1] == P.wavedec2(x, "db3", level=3)[0].shape[-1]
+    with pytest.raises(ValueError):
+        wt.fswaverec2((x, (x, x, x)), "db3")

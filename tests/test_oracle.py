@@ -188,3 +188,28 @@ def test_builtin_wavelet_table_is_orthonormal():
     assert np.abs(np.array(REC_LO["sym4"]) - sym4).max() < 1e-11
     w = BuiltinWavelet("db2", REC_LO["db2"])
     assert w.dec_lo == w.rec_lo[::-1] and w.dec_hi == w.rec_hi[::-1]
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference only exists in the build container")
+def test_separable_containers_are_a_repackaging_of_wavedec2_3():
+    """The claim behind pytorch_wavelet_toolbox_b200.separable: the reference's fswavedec2/3 bands equal
+    the wavedec2/3 bands ('da' = horizontal, 'ad' = vertical, 'dd' = diagonal; 3-D keys unchanged)."""
+    ptwt = import_reference()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 33, 40, generator=g, dtype=torch.float64)
+    for mode in ("zero", "reflect", "constant", "periodic"):
+        fs = ptwt.fswavedec2(x, "db2", mode=mode, level=2)
+        wd = P.wavedec2(x, "db2", mode=mode, level=2)
+        assert (fs[0] - wd[0]).abs().max() < 1e-12
+        for d, t in zip(fs[1:], wd[1:]):
+            assert list(d.keys()) == ["da", "ad", "dd"]
+            assert (d["da"] - t.horizontal).abs().max() < 1e-12
+            assert (d["ad"] - t.vertical).abs().max() < 1e-12
+            assert (d["dd"] - t.diagonal).abs().max() < 1e-12
+        assert (ptwt.fswaverec2(fs, "db2") - P.waverec2(wd, "db2")).abs().max() < 1e-12
+    x3 = torch.randn(2, 12, 13, 14, generator=g, dtype=torch.float64)
+    fs = ptwt.fswavedec3(x3, "db2", mode="zero", level=1)
+    wd = P.wavedec3(x3, "db2", mode="zero", level=1)
+    assert list(fs[1].keys()) == ["daa", "ada", "dda", "aad", "dad", "add", "ddd"]
+    for k in fs[1]:
+        assert (fs[1][k] - wd[1][k]).abs().max() < 1e-12
