@@ -172,7 +172,11 @@ def _analysis(data: torch.Tensor, wavelet: Any, mode: Optional[str], level: Opti
     for lv in plan.levels:
         check_pad_feasible(mode, cur, filt_len)
         cur = lv.dims
-    _no_autograd(data, wavelet=wav)
+    if torch.is_grad_enabled() and (x.requires_grad or any_requires_grad(wav)):
+        from ._autograd import analysis_with_grad
+
+        approx, details = analysis_with_grad(x, dec_lo, dec_hi, mode, level, ndim, _compute_device(x))
+        return approx, details, f
 
     dev = _compute_device(x)
     on_host = not x.is_cuda
@@ -420,7 +424,12 @@ def _synthesis(approx: torch.Tensor, levels_in: list[list[torch.Tensor]], probes
         cur = full
     if filt_len < 2 or filt_len > N.WT_MAX_FILT_LEN or len(rec_hi) != filt_len:
         raise ValueError(f"filter length {filt_len} not supported (2..{N.WT_MAX_FILT_LEN})")
-    _no_autograd(approx, *[t for lv in levels_in for t in lv], wavelet=wav)
+    if torch.is_grad_enabled() and (
+        approx.requires_grad or any(t.requires_grad for lv in levels_in for t in lv) or any_requires_grad(wav)
+    ):
+        from ._autograd import synthesis_with_grad
+
+        return synthesis_with_grad(approx, levels_in, probes, rec_lo, rec_hi, ndim, _compute_device(approx))
 
     dev = _compute_device(approx)
     on_host = not approx.is_cuda

@@ -325,12 +325,77 @@ def test_empty_batch_and_single_sample():
     _cmp_tree(wt.wavedec(one.to(DEV), "haar", mode="zero", level=1), P.wavedec(one, "haar", mode="zero", level=1), "len 2")
 
 
-def test_requires_grad_is_rejected_loudly():
-    x = torch.randn(2, 32, device=DEV, requires_grad=True)
+def _weighted_sum(coeffs, seed):
+    g = torch.Generator().manual_seed(seed)
+    tot = 0.0
+    for t in flatten_coeffs(coeffs):
+        w = torch.randn(t.shape, generator=g, dtype=torch.float64).to(t.device, t.dtype)
+        tot = tot + (t * w).sum()
+    return tot
+
+
+@pytest.mark.parametrize("mode", ["zero", "reflect", "constant", "periodic", "symmetric"])
+def test_autograd_matches_the_reference_operators(mode):
+    """gradients w.r.t. the data through wavedec*/waverec* equal those of the
+    reference's torch-operator chain (the oracle port under torch autograd, float64)."""
+    g = torch.Generator().manual_seed(31)
+    cases = [
+        (wt.wavedec, P.wavedec, wt.waverec, P.waverec, torch.randn(3, 41, generator=g, dtype=torch.float64), "db3", 2),
+        (wt.wavedec2, P.wavedec2, wt.waverec2, P.waverec2, torch.randn(2, 30, 37, generator=g, dtype=torch.float64), "db2", 2),
+        (wt.wavedec3, P.wavedec3, wt.waverec3, P.waverec3, torch.randn(2, 12, 15, 14, generator=g, dtype=torch.float64), "db2", 1),
+    ]
+    for fwd, pfwd, inv, pinv, x, wav, level in cases:
+        xa = x.clone().requires_grad_(True)
+        xb = x.clone().requires_grad_(True)
+        ca = fwd(xa.to(DEV), wav, mode=mode, level=level)
+        cb = pfwd(xb, wav, mode=mode, level=level)
+        for a, b in zip(flatten_coeffs(ca), flatten_coeffs(cb)):
+            assert_close_rel(a, b, scale=10.0, what=f"forward under grad {mode}")
+        _weighted_sum(ca, 5).backward()
+        _weighted_sum(cb, 5).backward()
+        assert_close_rel(xa.grad, xb.grad, scale=10.0, what=f"grad of {fwd.__name__} {mode}")
+        # synthesis: gradients w.r.t. every coefficient tensor
+        la = [t.detach().clone().requires_grad_(True) for t in flatten_coeffs(cb)]
+        lb = [t.detach().clone().requires_grad_(True) for t in flatten_coeffs(cb)]
+
+        def rebuild(flat, like):
+            out, i = [flat[0]], 1
+            for el in like[1:]:
+                if isinstance(el, torch.Tensor):
+                    out.append(flat[i]); i += 1
+                elif isinstance(el, dict):
+                    out.append(dict(zip(el.keys(), flat[i:i + 7]))); i += 7
+                else:
+                    out.append(type(el)(*flat[i:i + 3])); i += 3
+            return out if isinstance(like, list) else tuple(out)
+
+        ya = inv(rebuild([t.to(DEV) for t in la], cb), wav)
+        yb = pinv(rebuild(lb, cb), wav)
+        assert_close_rel(ya, yb, scale=10.0, what="inverse under grad")
+        w = torch.randn(yb.shape, generator=g, dtype=torch.float64)
+        (ya * w.to(DEV)).sum().backward()
+        (yb * w).sum().backward()
+        for a, b in zip(la, lb):
+            assert_close_rel(a.grad, b.grad, scale=10.0, what=f"grad of {inv.__name__}")
+
+
+def test_autograd_cpu_leaf_and_filter_grads_rejected():
+    x = torch.randn(2, 64, requires_grad=True)
+    c = wt.wavedec(x, "db2", level=2)            # CPU leaf: staged to the GPU, gradients come back on the CPU
+    sum(t.sum() for t in c).backward()
+    xr = x.detach().clone().requires_grad_(True)
+    sum(t.sum() for t in P.wavedec(xr, "db2", level=2)).backward()
+    assert x.grad.device.type == "cpu" and torch.allclose(x.grad, xr.grad, atol=1e-5)
+    from pytorch_wavelet_toolbox_b200._wavelets import as_wavelet
+
+    tt = wt.WaveletTensorTuple.from_wavelet(as_wavelet("db2"), torch.float32)
+    learn = wt.WaveletTensorTuple(*[t.clone().requires_grad_(True) for t in tt])
     with pytest.raises(NotImplementedError):
-        wt.wavedec(x, "haar", level=1)
+        wt.wavedec(torch.randn(2, 64, device=DEV), learn, level=1)
     with torch.no_grad():
-        wt.wavedec(x, "haar", level=1)
+        wt.wavedec(torch.randn(2, 64, device=DEV), learn, level=1)
+    with pytest.raises(NotImplementedError):
+        wt.MatrixWavedec("haar", 2)(torch.randn(2, 32, device=DEV, requires_grad=True))
 
 
 def test_host_pipeline_equals_device_path(monkeypatch):
