@@ -462,3 +462,53 @@ def test_separable_front_ends():
     assert wt.fswavedec2(x.to(DEV), "db3")[0].shape[-1] == P.wavedec2(x, "db3", level=3)[0].shape[-1]
     with pytest.raises(ValueError):
         wt.fswaverec2((x, (x, x, x)), "db3")
+
+
+def test_long_and_odd_filters_take_the_general_kernels():
+    """Filters the fused kernels do not cover (L > 16, odd L) run on the general kernels and still match."""
+    g = torch.Generator().manual_seed(41)
+    x1 = torch.randn(3, 300, generator=g, dtype=torch.float64)
+    for wav in ("db10", "db20"):
+        _cmp_tree(wt.wavedec(x1.to(DEV), wav, level=2, mode="symmetric"), P.wavedec(x1, wav, level=2, mode="symmetric"), wav)
+        c = wt.wavedec(x1.to(DEV), wav, level=2, mode="zero")
+        assert_close_rel(wt.waverec(c, wav)[..., :300], x1, scale=10.0, what=f"{wav} round trip")
+    x2 = torch.randn(2, 90, 100, generator=g)
+    _cmp_tree(wt.wavedec2(x2.to(DEV), "db10", level=2), P.wavedec2(x2, "db10", level=2), "db10 2d")
+    assert_close_rel(wt.waverec2(wt.wavedec2(x2.to(DEV), "db10", level=2), "db10"), P.waverec2(P.wavedec2(x2, "db10", level=2), "db10"),
+                     scale=10.0, what="db10 2d inverse")
+
+    class Odd5:  # odd-length custom filter bank (padding amounts follow the reference's formula for any L)
+        name = "odd5"
+        filter_bank = ([0.1, 0.2, 0.4, 0.2, 0.1], [-0.1, 0.3, -0.4, 0.3, -0.1], [0.1, 0.2, 0.4, 0.2, 0.1], [0.1, -0.3, 0.4, -0.3, 0.1])
+        dec_lo, dec_hi, rec_lo, rec_hi = filter_bank
+        dec_len = rec_len = 5
+
+        def __len__(self):
+            return 5
+
+    _cmp_tree(wt.wavedec(x1.to(DEV), Odd5(), level=2, mode="zero"), P.wavedec(x1, Odd5(), level=2, mode="zero"), "odd filter")
+    _cmp_tree(wt.wavedec2(x2.to(DEV), Odd5(), level=1, mode="constant"), P.wavedec2(x2, Odd5(), level=1, mode="constant"), "odd filter 2d")
+
+
+def test_config5_geometry_db8_level5():
+    """BASELINE.json configs[4] per-sample geometry (2048x2048 float32, db8, level 5) on 2 images."""
+    g = torch.Generator(device=DEV).manual_seed(55)
+    x = torch.randn(2, 2048, 2048, generator=g, device=DEV)
+    c = wt.wavedec2(x, "db8", level=5)
+    assert [lv.horizontal.shape[-1] for lv in c[1:]] == [78, 142, 269, 523, 1031] and c[0].shape[-1] == 78
+    want = P.wavedec2(x[:1].cpu(), "db8", level=5)
+    scale = max(float(t.abs().max()) for t in flatten_coeffs(want))
+    for a, b in zip(flatten_coeffs(c), flatten_coeffs(want)):
+        assert_close_rel(a[:1], b, scale=scale, what="cfg5 coefficients")
+    assert float((wt.waverec2(c, "db8") - x).abs().max()) < 5e-5
+
+
+def test_tiny_and_ragged_shapes():
+    g = torch.Generator().manual_seed(43)
+    for shape in ((1, 8, 9), (3, 9, 8), (2, 7, 130), (1, 131, 6)):
+        x = torch.randn(shape, generator=g, dtype=torch.float64)
+        for mode in ("zero", "symmetric", "constant"):
+            _cmp_tree(wt.wavedec2(x.to(DEV), "db2", level=1, mode=mode), P.wavedec2(x, "db2", level=1, mode=mode), f"tiny {shape} {mode}")
+            _cmp_tree(wt.wavedec2(x.float().to(DEV), "db2", level=1, mode=mode), P.wavedec2(x.float(), "db2", level=1, mode=mode), f"tiny f32 {shape}")
+    v = torch.randn(2, 5, 6, 70, generator=g)
+    _cmp_tree(wt.wavedec3(v.to(DEV), "haar", level=1, mode="symmetric"), P.wavedec3(v, "haar", level=1, mode="symmetric"), "thin volume")
