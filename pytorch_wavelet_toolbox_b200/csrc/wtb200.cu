@@ -43,6 +43,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 #ifndef WTB_NO_FUSED
 #include "fused2d.cuh"
 #include "fused2d_pair.cuh"
+#include "fused2d_mega.cuh"
 #include "inv2d.cuh"
 #include "fwd3d.cuh"
 #include "inv3d.cuh"
@@ -406,6 +407,17 @@ static int dwt_fwd_t(int ndim, int mode, int levels, int L, const double* dlo, c
             int rc = fused3d_fwd_try(mode, levels, L, dlo, dhi, (const float*)x, batch, dims, xs, xbs, lv, st, &done);
             if (rc != 0 || done) return rc;
         }
+        if (ndim == 2 && mega2d_enabled() && fused2d_fwd_covers(ndim, L) && xs[1] == 1) {
+            int done = 0, rc = 0;
+            switch (L) {
+                case 2: rc = launch_fwd2d_mega<2>(mode, levels, dlo, dhi, (const float*)x, batch, dims, xs, xbs, lv, ws, ws_bytes, st, &done); break;
+                case 4: rc = launch_fwd2d_mega<4>(mode, levels, dlo, dhi, (const float*)x, batch, dims, xs, xbs, lv, ws, ws_bytes, st, &done); break;
+                case 6: rc = launch_fwd2d_mega<6>(mode, levels, dlo, dhi, (const float*)x, batch, dims, xs, xbs, lv, ws, ws_bytes, st, &done); break;
+                case 8: rc = launch_fwd2d_mega<8>(mode, levels, dlo, dhi, (const float*)x, batch, dims, xs, xbs, lv, ws, ws_bytes, st, &done); break;
+                default: break;
+            }
+            if (rc != 0 || done) return rc;
+        }
     }
     {
         int rc = fused2d_fwd_try<T>(ndim, mode, levels, L, dlo, dhi, (const T*)x, batch, dims, xs, xbs, lv,
@@ -639,8 +651,9 @@ size_t wt_dwt_workspace_bytes(int ndim, int dtype, int levels, int filt_len, int
 #ifndef WTB_NO_FUSED
     if (!inverse && fused2d_fwd_covers(ndim, filt_len)) {
         // the fused path needs no scratch unless it has to bail out (odd strides); keep the
-        // general path's requirement only when the fused path is disabled
-        return 0;
+        // general path's requirement only when the fused path is disabled.  The persistent multi-level
+        // kernel keeps its work-queue and completion counters in the workspace.
+        return (dtype == WT_F32 && mega2d_enabled()) ? mega_workspace_bytes(levels, batch) : 0;
     }
     if (inverse && fused2d_inv_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len)) return 0;
     if (!inverse && fused3d_fwd_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len) && batch <= 65535) return 0;

@@ -512,3 +512,18 @@ def test_tiny_and_ragged_shapes():
             _cmp_tree(wt.wavedec2(x.float().to(DEV), "db2", level=1, mode=mode), P.wavedec2(x.float(), "db2", level=1, mode=mode), f"tiny f32 {shape}")
     v = torch.randn(2, 5, 6, 70, generator=g)
     _cmp_tree(wt.wavedec3(v.to(DEV), "haar", level=1, mode="symmetric"), P.wavedec3(v, "haar", level=1, mode="symmetric"), "thin volume")
+
+
+def test_persistent_multilevel_kernel_when_enabled(monkeypatch):
+    """The experimental persistent all-levels kernel (WTB200_MEGA=1: work queue + completion counters +
+    TMA reads of data written by other SMs) must agree with the oracle, for every boundary mode."""
+    monkeypatch.setenv("WTB200_MEGA", "1")
+    g = torch.Generator().manual_seed(61)
+    for mode in MODES:
+        for shape, lev in (((5, 300, 200), 3), ((3, 640, 520), 4), ((9, 64, 96), 2)):
+            x = torch.randn(shape, generator=g)
+            try:
+                want = P.wavedec2(x, "db4", mode=mode, level=lev)
+            except RuntimeError:
+                continue
+            _cmp_tree(wt.wavedec2(x.to(DEV), "db4", mode=mode, level=lev), want, f"mega {mode} {shape}")
