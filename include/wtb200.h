@@ -166,7 +166,9 @@ int wt_matrix_fwd(int dtype, int levels, int filt_len,
  * source, i.e. pass rec_lo / rec_hi un-flipped (reference flips them itself,
  * matmul_transform.py:110-112); blocks are the boundary rows of S^T per level with the
  * same layout as above.  next_len[l] is the number of samples kept from the level-l
- * reconstruction (n[l] or n[l]-1, reference matmul_transform.py:691-699). */
+ * reconstruction (n[l] or n[l]-1, reference matmul_transform.py:691-699).  allow_fused as in
+ * wt_matrix_fwd: non-zero lets groups of untrimmed levels run as one kernel that keeps the
+ * intermediate approximations on chip and drops the cross-corner round-off entries. */
 int wt_matrix_inv(int dtype, int levels, int filt_len,
                   const double* rec_lo, const double* rec_hi,
                   const int64_t* n, const int64_t* next_len,
@@ -175,7 +177,7 @@ int wt_matrix_inv(int dtype, int levels, int filt_len,
                   const void* lo_in, int64_t lo_stride,
                   const void* const* hi_in, const int64_t* hi_stride,
                   int64_t batch, void* y, int64_t y_stride,
-                  void* scratch, size_t scratch_bytes, void* stream);
+                  void* scratch, size_t scratch_bytes, int allow_fused, void* stream);
 
 /* Counters for bench.py's gpu_launches claim: kernels launched by this library on this
  * process since the last reset. */

@@ -142,4 +142,137 @@ __global__ void __launch_bounds__(256) mat_inv_kernel(const __grid_constant__ Ma
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-blocked synthesis level of the matrix transform.
+//
+// Interior of  y = S [lo; hi]  (reference src/ptwt/matmul_transform.py:682-699): with even L,
+//   y[t] = sum_i rec_lo[t + L/2 - 1 - 2 i] lo[i] + rec_hi[...] hi[i].
+// A thread produces OPT consecutive samples starting at t0 = OPT * (global thread index): the
+// coefficients it needs are the contiguous window i = t0/2 - C .. t0/2 - C + NCW - 1 of both bands
+// (128-bit loads, compile-time tap indices).  Threads whose samples or window touch an
+// orthogonalised boundary row / the dense corner blocks evaluate them sample by sample exactly
+// like mat_inv_kernel.
+// ------------------------------------------------------------------------------------------
+template <typename T> struct MatInvCfg;
+template <> struct MatInvCfg<float> { static constexpr int OPT = 8, VEC = 4; using V = float4; };
+template <> struct MatInvCfg<double> { static constexpr int OPT = 4, VEC = 2; using V = double2; };
+
+template <typename T>
+__device__ __forceinline__ T mat_inv_sample(const MatInvParams<T>& p, const T* __restrict__ lb, const T* __restrict__ hb,
+                                            int64_t t) {
+    const int64_t half = p.n / 2;
+    T acc = T(0);
+    int64_t i0 = (t - p.shift + 1) >> 1;
+    int64_t i1 = (t - p.shift + p.L - 1) >> 1;
+    if (i0 < p.nb_top) i0 = p.nb_top;
+    if (i1 > half - p.nb_bot - 1) i1 = half - p.nb_bot - 1;
+    for (int64_t i = i0; i <= i1; ++i) {
+        const int m = (int)(2 * i + p.shift - t);
+        acc = fma(p.taps.lo[m], __ldg(lb + i), acc);
+        acc = fma(p.taps.hi[m], __ldg(hb + i), acc);
+    }
+    const int nb = p.nb_top + p.nb_bot;
+    if (t < p.w_left) {
+        for (int r = 0; r < nb; ++r) {
+            const int64_t i = r < p.nb_top ? r : half - p.nb_bot + (r - p.nb_top);
+            acc = fma(__ldg(p.lo_left + r * p.w_left + t), __ldg(lb + i), acc);
+            acc = fma(__ldg(p.hi_left + r * p.w_left + t), __ldg(hb + i), acc);
+        }
+    }
+    const int64_t c0 = p.n - p.w_right;
+    if (t >= c0) {
+        const int64_t c = t - c0;
+        for (int r = 0; r < nb; ++r) {
+            const int64_t i = r < p.nb_top ? r : half - p.nb_bot + (r - p.nb_top);
+            acc = fma(__ldg(p.lo_right + r * p.w_right + c), __ldg(lb + i), acc);
+            acc = fma(__ldg(p.hi_right + r * p.w_right + c), __ldg(hb + i), acc);
+        }
+    }
+    return acc;
+}
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256) mat_inv_fast_kernel(const __grid_constant__ MatInvParams<T> p) {
+    using Cfg = MatInvCfg<T>;
+    using V = typename Cfg::V;
+    constexpr int OPT = Cfg::OPT, VEC = Cfg::VEC;
+    constexpr int C = ((L / 4) + VEC - 1) / VEC * VEC;                 // window starts at t0/2 - C
+    constexpr int NCW0 = C + (OPT + L / 2 - 2) / 2 + 1;
+    constexpr int NCV = (NCW0 + VEC - 1) / VEC;
+    constexpr int NCW = NCV * VEC;
+    const int64_t t0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * OPT;
+    if (t0 >= p.keep) return;
+    const int64_t b = blockIdx.y;
+    const T* __restrict__ lb = p.lo + b * p.lo_stride;
+    const T* __restrict__ hb = p.hi + b * p.hi_stride;
+    T* __restrict__ yb = p.y + b * p.y_stride;
+    const int64_t half = p.n / 2;
+    const int64_t ilo = t0 / 2 - C;
+    T out[OPT];
+    const bool fast = ilo >= p.nb_top && ilo + NCW <= half - p.nb_bot && t0 >= p.w_left && t0 + OPT <= p.n - p.w_right;
+    if (fast) {
+        T a[NCW], d[NCW];
+#pragma unroll
+        for (int q = 0; q < NCV; ++q) {
+            const V u = __ldg(reinterpret_cast<const V*>(lb + ilo) + q);
+            const V w = __ldg(reinterpret_cast<const V*>(hb + ilo) + q);
+            const T* up = reinterpret_cast<const T*>(&u);
+            const T* wp = reinterpret_cast<const T*>(&w);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { a[VEC * q + e] = up[e]; d[VEC * q + e] = wp[e]; }
+        }
+#pragma unroll
+        for (int g = 0; g < OPT; ++g) {
+            T acc = T(0);
+#pragma unroll
+            for (int w = 0; w < NCW; ++w) {
+                // rec index k = t + L/2 - 1 - 2 i with t = t0 + g, i = t0/2 - C + w; taps are stored flipped
+                const int k = g + L / 2 - 1 + 2 * C - 2 * w;
+                if (k >= 0 && k < L) {
+                    acc = fma(p.taps.lo[L - 1 - k], a[w], acc);
+                    acc = fma(p.taps.hi[L - 1 - k], d[w], acc);
+                }
+            }
+            out[g] = acc;
+        }
+    } else {
+        for (int g = 0; g < OPT; ++g) out[g] = (t0 + g < p.keep) ? mat_inv_sample(p, lb, hb, t0 + g) : T(0);
+    }
+    if (t0 + OPT <= p.keep) {
+#pragma unroll
+        for (int q = 0; q < OPT / VEC; ++q) {
+            V v;
+            T* vp = reinterpret_cast<T*>(&v);
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) vp[e] = out[VEC * q + e];
+            reinterpret_cast<V*>(yb + t0)[q] = v;
+        }
+    } else {
+        for (int g = 0; g < OPT && t0 + g < p.keep; ++g) yb[t0 + g] = out[g];
+    }
+}
+
+template <typename T>
+static bool launch_mat_inv_fast(const MatInvParams<T>& p, cudaStream_t st, cudaError_t* err) {
+    using Cfg = MatInvCfg<T>;
+    constexpr int OPT = Cfg::OPT, VEC = Cfg::VEC;
+    *err = cudaSuccess;
+    const int L = p.L;
+    if ((L & 1) || L < 2 || L > 16 || p.batch > 65535 || p.keep <= 0) return false;
+    if (p.shift != L / 2) return false;
+    if (((uintptr_t)p.lo & 15) || ((uintptr_t)p.hi & 15) || ((uintptr_t)p.y & 15)) return false;
+    if ((p.lo_stride % VEC) || (p.hi_stride % VEC) || (p.y_stride % VEC)) return false;
+    const int64_t nblk = (p.keep + (int64_t)OPT * 256 - 1) / ((int64_t)OPT * 256);
+    if (nblk > 0x7fffffff) return false;
+    dim3 grid((unsigned)nblk, (unsigned)p.batch);
+#define WTB_MI(LL) case LL: mat_inv_fast_kernel<T, LL><<<grid, 256, 0, st>>>(p); break;
+    switch (L) {
+        WTB_MI(2) WTB_MI(4) WTB_MI(6) WTB_MI(8) WTB_MI(10) WTB_MI(12) WTB_MI(14) WTB_MI(16)
+        default: return false;
+    }
+#undef WTB_MI
+    *err = cudaGetLastError();
+    return true;
+}
+
 }  // namespace wtb

@@ -505,7 +505,9 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
         if (allow_fused && !getenv("WTB200_DISABLE_FUSED")) {
             // group of consecutive unpadded levels -> one fused launch
             int k = 0;
-            while (l + k < levels && k < MATF_MAXK && !padded[l + k] && !(n[l + k] & 1) &&
+            int kmax = 4;  // measured on config 4 (tools/ab_matrix.py): 4 levels x 4096-sample chunks beat 6 x 4096
+            if (const char* ev = getenv("WTB200_MATF_K")) { const int v = atoi(ev); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
+            while (l + k < levels && k < kmax && !padded[l + k] && !(n[l + k] & 1) &&
                    (k == 0 || n[l + k] == n[l + k - 1] / 2))
                 ++k;
             if (k >= 2) {
@@ -573,7 +575,7 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
                         const int64_t* next_len, const int32_t* nbt, const int32_t* nbb, const int32_t* wt,
                         const int32_t* wb, const void* blocks, const void* lo_in, int64_t lo_stride,
                         const void* const* hi_in, const int64_t* hi_stride, int64_t batch, void* y,
-                        int64_t ys, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+                        int64_t ys, void* scratch, size_t scratch_bytes, int allow_fused, cudaStream_t st) {
     Taps<T> taps;
     fill_taps(taps, rlo, rhi, L, true);  // rows of S^T carry the flipped rec filters
     const size_t need = levels > 1 ? (size_t)2 * batch * n[0] * sizeof(T) : 0;
@@ -589,7 +591,45 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
     const T* src = (const T*)lo_in;
     int64_t src_stride = lo_stride;
     T* ping[2] = {(T*)scratch, (T*)scratch + batch * n[0]};
+    int pp = 0;  // scratch half the next intermediate result goes to
+    const T* bptr[4 * 64];
+    for (int l = 0; l < levels; ++l) {
+        const T* q = (const T*)blocks + off[l];
+        const int64_t nb = (int64_t)nbt[l] + nbb[l];
+        bptr[4 * l] = q; q += nb * wt[l];
+        bptr[4 * l + 1] = q; q += nb * wb[l];
+        bptr[4 * l + 2] = q; q += nb * wt[l];
+        bptr[4 * l + 3] = q;
+    }
     for (int l = levels - 1; l >= 0; --l) {
+        if (allow_fused && !getenv("WTB200_DISABLE_FUSED")) {
+            // group of levels l, l-1, ..., l-k+1 whose intermediate results are not trimmed -> one launch
+            // default 1 = per-level kernels: on config 4 the fused synthesis kernel (0.79 ms) is slower than
+            // twelve register-blocked per-level launches (0.57 ms); WTB200_MATI_K >= 2 opts in
+            int kmax = 1;
+            if (const char* ev = getenv("WTB200_MATI_K")) { const int v = atoi(ev); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
+            int k = 1;
+            while (k < kmax && l - k >= 0 && next_len[l - k + 1] == n[l - k + 1] && n[l - k] == 2 * n[l - k + 1]) ++k;
+            if (k >= 2) {
+                const int lf = l - k + 1;  // finest level of the group
+                const bool last = (lf == 0);
+                const int64_t keep0 = next_len[lf];
+                const int64_t keep4 = (keep0 + 3) & ~int64_t(3);
+                T* dst = last ? (T*)y : ping[pp];
+                const int64_t dst_stride = last ? ys : (keep4 <= n[0] ? keep4 : keep0);
+                cudaError_t e = cudaSuccess;
+                if ((keep0 == n[lf] || keep0 == n[lf] - 1) &&
+                    launch_mat_inv_fused<T>(L, k, n + lf, keep0, nbt + lf, nbb + lf, wt + lf, wb + lf, bptr + 4 * lf, src,
+                                            src_stride, hi_in + lf, hi_stride + lf, batch, dst, dst_stride, rlo, rhi, st, &e)) {
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                    if (e != cudaSuccess) return cuda_fail(e, "mat_inv_fused_kernel");
+                    src = dst; src_stride = dst_stride;
+                    if (!last) pp ^= 1;
+                    l = lf;
+                    continue;
+                }
+            }
+        }
         MatInvParams<T> p;
         p.lo = src; p.lo_stride = src_stride;
         p.hi = (const T*)hi_in[l]; p.hi_stride = hi_stride[l];
@@ -597,8 +637,10 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
         if (!(p.keep == p.n || p.keep == p.n - 1))
             return fail(WT_ESHAPE, "level %d: keep %lld of %lld samples", l + 1, (long long)p.keep, (long long)p.n);
         const bool last = (l == 0);
-        p.y = last ? (T*)y : ping[l & 1];
-        p.y_stride = last ? ys : p.keep;
+        p.y = last ? (T*)y : ping[pp];
+        // intermediate rows start on 16-byte boundaries (vector loads of the next level) when they fit
+        const int64_t keep4 = (p.keep + 3) & ~int64_t(3);
+        p.y_stride = last ? ys : (keep4 <= n[0] ? keep4 : p.keep);
         p.L = L; p.shift = L / 2 + (L % 2);
         p.nb_top = nbt[l]; p.nb_bot = nbb[l]; p.w_left = wt[l]; p.w_right = wb[l];
         const T* blk = (const T*)blocks + off[l];
@@ -610,12 +652,17 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
         p.taps = taps;
         const int64_t total = batch * p.keep;
         if (total > 0) {
-            mat_inv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+            cudaError_t e = cudaSuccess;
+            const bool fast = !getenv("WTB200_DISABLE_FUSED") && launch_mat_inv_fast<T>(p, st, &e);
+            if (!fast) {
+                mat_inv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+                e = cudaGetLastError();
+            }
             g_launches.fetch_add(1, std::memory_order_relaxed);
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) return cuda_fail(e, "mat_inv_kernel");
+            if (e != cudaSuccess) return cuda_fail(e, fast ? "mat_inv_fast_kernel" : "mat_inv_kernel");
         }
         src = p.y; src_stride = p.y_stride;
+        if (!last) pp ^= 1;
     }
     return 0;
 }
@@ -725,7 +772,7 @@ int wt_matrix_inv(int dtype, int levels, int filt_len, const double* rec_lo, con
                   const int64_t* n, const int64_t* next_len, const int32_t* nb_top, const int32_t* nb_bot,
                   const int32_t* w_left, const int32_t* w_right, const void* blocks, const void* lo_in,
                   int64_t lo_stride, const void* const* hi_in, const int64_t* hi_stride, int64_t batch, void* y,
-                  int64_t y_stride, void* scratch, size_t scratch_bytes, void* stream) {
+                  int64_t y_stride, void* scratch, size_t scratch_bytes, int allow_fused, void* stream) {
     if (dtype != WT_F32 && dtype != WT_F64) return fail(WT_EINVAL, "dtype must be WT_F32 or WT_F64");
     if (levels < 1) return fail(WT_EINVAL, "levels must be >= 1");
     if (filt_len < 2 || filt_len > WT_MAX_FILT_LEN) return fail(WT_EUNSUPPORTED, "filter length %d", filt_len);
@@ -737,10 +784,10 @@ int wt_matrix_inv(int dtype, int levels, int filt_len, const double* rec_lo, con
     if (dtype == WT_F32)
         return matrix_inv_t<float>(levels, filt_len, rec_lo, rec_hi, n, next_len, nb_top, nb_bot, w_left, w_right,
                                    blocks, lo_in, lo_stride, hi_in, hi_stride, batch, y, y_stride, scratch,
-                                   scratch_bytes, st);
+                                   scratch_bytes, allow_fused, st);
     return matrix_inv_t<double>(levels, filt_len, rec_lo, rec_hi, n, next_len, nb_top, nb_bot, w_left, w_right,
                                 blocks, lo_in, lo_stride, hi_in, hi_stride, batch, y, y_stride, scratch,
-                                scratch_bytes, st);
+                                scratch_bytes, allow_fused, st);
 }
 
 uint64_t wt_launch_count(void) { return g_launches.load(); }

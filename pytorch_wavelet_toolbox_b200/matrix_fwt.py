@@ -297,6 +297,7 @@ class _BlockStore:
         self.key = None
         self.levels: list[_LevelBlocks] = []
         self.device_flat: Optional[torch.Tensor] = None
+        self._fused_ok: Optional[int] = None
 
     def get(self, lo: np.ndarray, hi: np.ndarray, dtype, sizes: Sequence[int], method: str, dev: torch.device):
         key = (lo.tobytes(), hi.tobytes(), dtype, tuple(sizes), method, str(dev))
@@ -307,7 +308,14 @@ class _BlockStore:
                 flat = torch.zeros(1, dtype=dtype)
             self.device_flat = flat.to(dev)
             self.key = key
+            self._fused_ok = None
         return self.levels, self.device_flat
+
+    def allow_fused(self) -> int:
+        """1 when the cross-corner entries of every level are round-off (see FUSED_CROSS_CORNER_MAX)."""
+        if self._fused_ok is None:
+            self._fused_ok = 1 if _cross_corner_max(self.levels) <= FUSED_CROSS_CORNER_MAX else 0
+        return self._fused_ok
 
 
 class MatrixWavedec:
@@ -328,6 +336,7 @@ class MatrixWavedec:
         self._built = False
         self._dtype: Optional[torch.dtype] = None
         self._store = _BlockStore()
+        self._call_cache: Optional[dict] = None
         self._sparse_cache: Optional[list[torch.Tensor]] = None
         if self.orthogonalization not in _ORTH_METHODS:
             raise NotImplementedError
@@ -410,37 +419,46 @@ class MatrixWavedec:
             if xd.stride(-1) != 1 and xd.shape[-1] != 1:
                 xd = xd.contiguous()
             blocks, flat = self._store.get(lo_t, hi_t, dt, sizes, self.orthogonalization, dev)
+            # everything that depends only on (length, dtype, device) is prepared once per object
+            ck = (length, dt, str(dev), first_pad, self.odd_coeff_padding_mode, tuple(sizes))
+            cc = self._call_cache
+            if cc is None or cc["key"] != ck:
+                lens = [n // 2 for n in sizes]
+                offs = {}
+                o = lens[-1]
+                for l in range(nl - 1, -1, -1):
+                    offs[l] = o
+                    o += lens[l]
+                padded = [1 if p else 0 for p in self.pad_list]
+                padded[0] = 1 if first_pad else 0
+                cc = {
+                    "key": ck, "lens": lens, "offs": offs, "total": lens[-1] + sum(lens),
+                    "n": N.i64_array(sizes), "pd": N.i32_array(padded),
+                    "nbt": N.i32_array([b.nb_top for b in blocks]), "nbb": N.i32_array([b.nb_bot for b in blocks]),
+                    "wl": N.i32_array([b.w_left for b in blocks]), "wr": N.i32_array([b.w_right for b in blocks]),
+                    "lo": N.f64_array(lo_t), "hi": N.f64_array(hi_t),
+                    "mode": N.MODES[self.odd_coeff_padding_mode if (self.padded or first_pad) else "zero"],
+                    "fused": self._store.allow_fused(),
+                    "hi_ptrs": (C.c_void_p * nl)(), "hi_strides": (C.c_int64 * nl)(),
+                }
+                self._call_cache = cc
+            lens, offs = cc["lens"], cc["offs"]
             # packed output [batch, total]: [cA | cD_n | ... | cD_1]
-            lens = [n // 2 for n in sizes]
-            total = lens[-1] + sum(lens)
-            out = torch.empty((batch, total), dtype=dt, device=dev)
-            offs = {}
-            o = lens[-1]
-            for l in range(nl - 1, -1, -1):
-                offs[l] = o
-                o += lens[l]
+            out = torch.empty((batch, cc["total"]), dtype=dt, device=dev)
             es = out.element_size()
-            hi_ptrs = (C.c_void_p * nl)(*[out.data_ptr() + offs[l] * es for l in range(nl)])
-            hi_strides = (C.c_int64 * nl)(*([out.stride(0)] * nl))
-            padded = [1 if p else 0 for p in self.pad_list]
-            padded[0] = 1 if first_pad else 0
-            n_arr, n_p = N.i64_array(sizes)
-            pd_arr, pd_p = N.i32_array(padded)
-            nbt_arr, nbt_p = N.i32_array([b.nb_top for b in blocks])
-            nbb_arr, nbb_p = N.i32_array([b.nb_bot for b in blocks])
-            wt_arr, wt_p = N.i32_array([b.w_left for b in blocks])
-            wb_arr, wb_p = N.i32_array([b.w_right for b in blocks])
-            lo_arr, lo_p = N.f64_array(lo_t)
-            hi_arr, hi_p = N.f64_array(hi_t)
+            base, ostride = out.data_ptr(), out.stride(0)
+            hi_ptrs, hi_strides = cc["hi_ptrs"], cc["hi_strides"]
+            for l in range(nl):
+                hi_ptrs[l] = base + offs[l] * es
+                hi_strides[l] = ostride
             scratch_elems = 2 * batch * (sizes[0] // 2) if nl > 1 else 0
             scratch = torch.empty((max(scratch_elems, 1),), dtype=dt, device=dev)
             lib = N.load()
             rc = lib.wt_matrix_fwd(
-                _dtype_code(dt), nl, len(lo_t), lo_p, hi_p, n_p, pd_p,
-                N.MODES[self.odd_coeff_padding_mode if (self.padded or first_pad) else "zero"],
-                nbt_p, nbb_p, wt_p, wb_p, flat.data_ptr(), xd.data_ptr(), batch, xd.stride(0),
-                hi_ptrs, hi_strides, out.data_ptr(), out.stride(0),
-                scratch.data_ptr(), scratch_elems * es, 1 if _cross_corner_max(blocks) <= FUSED_CROSS_CORNER_MAX else 0,
+                _dtype_code(dt), nl, len(lo_t), cc["lo"][1], cc["hi"][1], cc["n"][1], cc["pd"][1], cc["mode"],
+                cc["nbt"][1], cc["nbb"][1], cc["wl"][1], cc["wr"][1], flat.data_ptr(), xd.data_ptr(), batch, xd.stride(0),
+                hi_ptrs, hi_strides, base, ostride,
+                scratch.data_ptr(), scratch_elems * es, cc["fused"],
                 torch.cuda.current_stream(dev).cuda_stream,
             )
             N.check(rc, "wt_matrix_fwd")
@@ -590,7 +608,8 @@ class MatrixWaverec:
             rc = lib.wt_matrix_inv(
                 _dtype_code(dt), nl, len(lo_t), lo_p, hi_p, n_p, k_p, nbt_p, nbb_p, wt_p, wb_p, flat.data_ptr(),
                 folded[0].data_ptr(), folded[0].stride(0), hi_ptrs, hi_strides, batch, y.data_ptr(), y.stride(0),
-                scratch.data_ptr(), scratch_elems * es, torch.cuda.current_stream(dev).cuda_stream,
+                scratch.data_ptr(), scratch_elems * es, self._store.allow_fused(),
+                torch.cuda.current_stream(dev).cuda_stream,
             )
             N.check(rc, "wt_matrix_inv")
             if on_host:

@@ -527,3 +527,62 @@ def test_persistent_multilevel_kernel_when_enabled(monkeypatch):
             except RuntimeError:
                 continue
             _cmp_tree(wt.wavedec2(x.to(DEV), "db4", mode=mode, level=lev), want, f"mega {mode} {shape}")
+
+
+def test_calls_can_be_captured_in_a_cuda_graph():
+    """No allocation, synchronisation or host round trip inside the native entry points: a whole transform
+    can be captured once and replayed (the way to run the small configurations without per-call host cost)."""
+    g = torch.Generator().manual_seed(71)
+    x2 = torch.randn((3, 200, 136), generator=g).to(DEV)
+    x1 = torch.randn((4, 1000), generator=g).to(DEV)
+    xm = torch.randn((4, 512), generator=g, dtype=torch.float64).to(DEV)
+    fw = wt.MatrixWavedec("db3", level=3)
+    iv = wt.MatrixWaverec("db3")
+    fw(xm)  # operator construction (QR on the host) happens outside the capture
+    iv(fw(xm))
+
+    def run():
+        c2 = wt.wavedec2(x2, "db4", level=3)
+        c1 = wt.wavedec(x1, "sym5", mode="symmetric", level=4)
+        cm = fw(xm)
+        return c2, wt.waverec2(c2, "db4"), c1, wt.waverec(c1, "sym5"), cm, iv(cm)
+
+    eager = run()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            captured = run()
+    # new input values, same buffers: the replay must recompute everything
+    x2.mul_(-2.0); x1.add_(1.0); xm.mul_(0.5)
+    graph.replay()
+    torch.cuda.synchronize()
+    fresh = run()
+    torch.cuda.synchronize()
+    def leaves(t):
+        if isinstance(t, torch.Tensor):
+            return [t]
+        if isinstance(t, dict):
+            return [v for k in sorted(t) for v in leaves(t[k])]
+        return [v for el in t for v in leaves(el)]
+
+    got, want = leaves(captured), leaves(fresh)
+    assert len(got) == len(want) and len(got) > 20
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    assert not torch.equal(leaves(eager)[0], want[0])
+
+
+def test_fused_matrix_synthesis_kernel_when_enabled(monkeypatch):
+    """WTB200_MATI_K >= 2 runs groups of synthesis levels as one kernel (intermediate approximations stay in
+    shared memory); it must agree with the oracle like the default per-level kernels."""
+    monkeypatch.setenv("WTB200_MATI_K", "4")
+    g = torch.Generator().manual_seed(83)
+    for wav, n, level in (("db2", 64, 3), ("db4", 256, 4), ("db6", 4096, 6), ("sym5", 1000, 5), ("haar", 48, 3),
+                          ("db3", 202, 4)):
+        x = torch.randn((5, n), generator=g, dtype=torch.float64)
+        want_c = P.MatrixWavedec(wav, level)(x)
+        want = P.MatrixWaverec(wav)(want_c)
+        got = wt.MatrixWaverec(wav)([t.to(DEV) for t in want_c])
+        assert_close_rel(got, want, scale=float(want.abs().max()), what=f"fused synthesis {wav} n={n} L{level}")
