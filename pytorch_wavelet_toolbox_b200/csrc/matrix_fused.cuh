@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) mat_fwd_fused_kernel(const __grid_constan
     constexpr int NE = (L + 2 + DELTA + 1) / 2;   // polyphase entries covering the window of an output pair
     constexpr int NEV = (NE + PQ + 1) / 2 * 2;    // rounded to whole 2-element vectors
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T* bufA = reinterpret_cast<T*>(smem_raw);     // even | odd arrays of the current level input
     const int capA = p.cap0 / 2 + 8;              // entries per polyphase array (level 0)
     T* bufB = bufA + 2 * capA;                    // even | odd arrays of the next level
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256) mat_inv_fused_kernel(const __grid_constan
     constexpr int H = L / 2;
     constexpr int C = (L / 4);                                     // window starts at t0/2 - C
     constexpr int NCW = C + (4 + H - 2) / 2 + 1;                   // coefficients in the window of 4 samples
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T* bufA = reinterpret_cast<T*>(smem_raw);
     T* bufB = bufA + p.cap;
     T* shi = bufB + p.cap;

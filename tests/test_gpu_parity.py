@@ -586,3 +586,20 @@ def test_fused_matrix_synthesis_kernel_when_enabled(monkeypatch):
         want = P.MatrixWaverec(wav)(want_c)
         got = wt.MatrixWaverec(wav)([t.to(DEV) for t in want_c])
         assert_close_rel(got, want, scale=float(want.abs().max()), what=f"fused synthesis {wav} n={n} L{level}")
+
+
+@pytest.mark.parametrize("tile", ["0", "1", "2"])
+def test_wavedec3_every_tile_shape(monkeypatch, tile):
+    """The 3-D analysis kernel is instantiated for three tile shapes (16x32, 11x44, 8x64); the host picks by
+    waste, WTB200_FWD3D_TILE forces one.  All must agree with the oracle on ragged extents and every mode."""
+    monkeypatch.setenv("WTB200_FWD3D_TILE", tile)
+    g = torch.Generator().manual_seed(97 + int(tile))
+    for mode in MODES:
+        for shape, wav, lev in (((2, 37, 50, 91), "sym4", 2), ((1, 20, 131, 45), "db2", 2), ((3, 16, 18, 140), "haar", 1)):
+            x = torch.randn(shape, generator=g)
+            try:
+                want = P.wavedec3(x, wav, mode=mode, level=lev)
+            except RuntimeError:
+                continue
+            got = wt.wavedec3(x.to(DEV), wav, mode=mode, level=lev)
+            _cmp_tree(got, want, f"tile {tile} {mode} {shape} {wav}")
