@@ -182,6 +182,8 @@ def main() -> None:
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip timing the reference algorithm on the GPU")
+    ap.add_argument("--incumbent-batch", type=int, default=16)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -329,6 +331,37 @@ def main() -> None:
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3}
         del oh, xh
 
+    # the incumbent on this GPU: the reference's own algorithm (F.pad -> F.conv2d(stride 2) with the four
+    # outer-product filters, per level) executed by torch/cuDNN on the same device -- what ptwt does today
+    # when it is handed CUDA tensors.  Informational: a sample of the batch, device-resident, CUDA events.
+    incumbent = None
+    if rank == 0 and not args.no_incumbent:
+        try:
+            sys.path.insert(0, str(Path(__file__).resolve().parent))
+            from oracle import ptwt_port as P
+
+            nb = min(args.incumbent_batch, B)
+            xs = x[:nb]
+            for _ in range(2):
+                ref_c = P.wavedec2(xs, WAVELET, mode=MODE, level=LEVEL)
+            torch.cuda.synchronize(dev)
+            j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            j0.record()
+            for _ in range(3):
+                ref_c = P.wavedec2(xs, WAVELET, mode=MODE, level=LEVEL)
+            j1.record()
+            torch.cuda.synchronize(dev)
+            inc_ms = j0.elapsed_time(j1) / 3
+            inc_alg = nb * algorithmic_bytes_per_image()
+            incumbent = {"value": nb * H * W / (inc_ms * 1e-3) / 1e6, "unit": "Msamples/s (1 GPU)", "ms": inc_ms,
+                         "sample": f"{nb} images of {H}x{W}, device resident",
+                         "step_frac": inc_alg / (inc_ms * 1e-3) / 1e9 / peak,
+                         "what": "reference algorithm (F.pad + F.conv2d stride 2, torch/cuDNN) on the same B200"}
+            del ref_c, xs
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            incumbent = {"unavailable": f"{type(ex).__name__}: {str(ex)[:160]}"}
+
     cpu = None
     if rank == 0 and not args.no_cpu:
         v, cores, times = cpu_reference_throughput(args.cpu_batch, 3)
@@ -352,7 +385,7 @@ def main() -> None:
                          "kernel_launches_timed": int(k_launches),
                          "step_achieved": step_achieved, "step_frac": step_achieved / peak,
                          "algorithmic_bytes_per_step": alg, "median_step_ms": med_ms, "min_step_ms": step_ms[0]},
-            "cpu_baseline": cpu, "e2e": e2e, "inverse": inverse, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "inverse": inverse, "incumbent_gpu": incumbent, "gpu_launches": int(launches), "clocks": clocks,
             "parity": {"max_rel_err_vs_oracle": max_err, "tolerance": 1e-5},
         }
         print(json.dumps(line))

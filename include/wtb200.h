@@ -18,6 +18,9 @@
  *                      (odd-length pad -> torch.sparse.mm(A_level, lo) -> split)
  *   wt_matrix_inv   <- MatrixWaverec.__call__ level loop, src/ptwt/matmul_transform.py:682-699
  *                      (cat -> torch.sparse.mm(S_level, .) -> trim)
+ *   wt_matrix_axis_fwd / wt_matrix_axis_inv
+ *                   <- the per-axis products of the separable MatrixWavedec2/3 and MatrixWaverec2/3,
+ *                      src/ptwt/matmul_transform_2.py:514-531, :797-806; matmul_transform_3.py:255-262, :476-479
  *
  * Conventions
  *   - plain C, no C++ / torch types; every function returns 0 on success, a negative
@@ -178,6 +181,30 @@ int wt_matrix_inv(int dtype, int levels, int filt_len,
                   const void* const* hi_in, const int64_t* hi_stride,
                   int64_t batch, void* y, int64_t y_stride,
                   void* scratch, size_t scratch_bytes, int allow_fused, void* stream);
+
+/* One level of the 1-D boundary-wavelet operator along an arbitrary axis of a [outer, n, inner]
+ * tensor whose inner index is contiguous -- the building block of the SEPARABLE 2-D / 3-D matrix
+ * transforms (reference src/ptwt/matmul_transform_2.py:514-531 "batch_mm(fwt_col_matrix, ...)",
+ * src/ptwt/matmul_transform_3.py:255-262 "_batch_dim_mm(mat, lll, dim)").
+ *   analysis:  x [outer, n - padded, inner] -> y [outer, n, inner], low-pass rows 0..n/2-1 then
+ *              high-pass rows n/2..n-1 along the axis (the reference's "A x, then split");
+ *              padded = 1 appends one sample along the axis per odd_mode first.
+ *   synthesis: x [outer, n, inner] (lo | hi along the axis) -> y [outer, keep, inner], keep <= n.
+ * blocks: device array, the level's boundary rows as in wt_matrix_fwd / wt_matrix_inv
+ * (lo_left, lo_right, hi_left, hi_right).  Strides are in elements. */
+int wt_matrix_axis_fwd(int dtype, int filt_len, const double* dec_lo, const double* dec_hi,
+                       int64_t n, int padded, int odd_mode,
+                       int nb_top, int nb_bot, int w_left, int w_right, const void* blocks,
+                       const void* x, int64_t outer, int64_t inner,
+                       int64_t x_outer_stride, int64_t x_axis_stride,
+                       void* y, int64_t y_outer_stride, int64_t y_axis_stride, void* stream);
+
+int wt_matrix_axis_inv(int dtype, int filt_len, const double* rec_lo, const double* rec_hi,
+                       int64_t n, int64_t keep,
+                       int nb_top, int nb_bot, int w_left, int w_right, const void* blocks,
+                       const void* x, int64_t outer, int64_t inner,
+                       int64_t x_outer_stride, int64_t x_axis_stride,
+                       void* y, int64_t y_outer_stride, int64_t y_axis_stride, void* stream);
 
 /* Counters for bench.py's gpu_launches claim: kernels launched by this library on this
  * process since the last reset. */

@@ -41,6 +41,14 @@ CASES = [
     ("matrix", "float64", "db2", "reflect", 3, (2, 101), None),        # odd lengths -> padded levels
     ("matrix", "float64", "sym5", "zero", 2, (4, 64), None),
     ("matrix_gs", "float64", "db4", "zero", 2, (2, 64), None),         # gramschmidt orthogonalisation
+    # separable 2-D / 3-D boundary-wavelet transforms; appended so that the
+    # random inputs of the cases above stay what they were
+    ("matrix2", "float64", "db2", "zero", 2, (2, 32, 24), None),
+    ("matrix2", "float64", "db3", "reflect", 2, (3, 33, 27), None),    # odd extents -> padded levels
+    ("matrix2", "float32", "haar", "zero", 3, (1, 32, 32), None),
+    ("matrix2", "float64", "sym4", "symmetric", 2, (2, 37, 3, 40), (1, 3)),
+    ("matrix3", "float64", "db2", "zero", 2, (2, 16, 20, 24), None),
+    ("matrix3", "float64", "haar", "constant", 2, (9, 10, 11), None),  # odd extents, no batch dimension
 ]
 
 
@@ -80,6 +88,14 @@ def main() -> None:
             kw = {} if axes is None else {"axes": axes}
             c = ptwt.wavedec3(x, wav, mode=mode, level=level, **kw)
             r = ptwt.waverec3(c, wav, **kw)
+        elif family == "matrix2":
+            kw = {} if axes is None else {"axes": axes}
+            c = ptwt.MatrixWavedec2(wav, level, odd_coeff_padding_mode=mode, **kw)(x)
+            r = ptwt.MatrixWaverec2(wav, **kw)(c)
+        elif family == "matrix3":
+            kw = {} if axes is None else {"axes": axes}
+            c = ptwt.MatrixWavedec3(wav, level, odd_coeff_padding_mode=mode, **kw)(x)
+            r = ptwt.MatrixWaverec3(wav, **kw)(c)
         else:
             meth = "gramschmidt" if family == "matrix_gs" else "qr"
             c = ptwt.MatrixWavedec(wav, level, orthogonalization=meth, odd_coeff_padding_mode=mode)(x)

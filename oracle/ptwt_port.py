@@ -157,7 +157,7 @@ def _axes(axes, ndim):
 def analysis_levels(x: torch.Tensor, wavelet: Any, mode: str, level: int, ndim: int):
     """x [B, d1..dN] -> (approx [B,..], [finest..coarsest: tensor [B, 2^ndim, ..] incl. band 0])."""
     dec_lo, dec_hi, _, _ = _taps(wavelet, x.dtype, flip=True)
-    filt = _nd_filters(dec_lo, dec_hi, ndim)
+    filt = _nd_filters(dec_lo, dec_hi, ndim).to(x.device)  # the reference builds its filters on data.device
     cur = x.unsqueeze(1)
     outs = []
     for _ in range(level):
@@ -172,7 +172,7 @@ def synthesis_levels(approx: torch.Tensor, levels: Sequence[Sequence[torch.Tenso
     """approx [B,..]; levels coarsest-first, each the 2^ndim - 1 detail bands in the reference's order."""
     _, _, rec_lo, rec_hi = _taps(wavelet, approx.dtype, flip=False)
     L = rec_lo.shape[0]
-    filt = _nd_filters(rec_lo, rec_hi, ndim)
+    filt = _nd_filters(rec_lo, rec_hi, ndim).to(approx.device)
     cur = approx
     base = (2 * L - 3) // 2
     for i, bands in enumerate(levels):
@@ -414,3 +414,121 @@ class MatrixWaverec:
                 lo = lo[:-1]
                 assert lo.shape[0] == rest[i + 1].shape[-1], "padding error"
         return _unfold(lo.T, 1, self.axis, shape)
+
+
+# ---------------------------------------------------------------------------------------------
+# separable 2-D / 3-D boundary-filter matrix FWT
+#   matmul_transform_2.py:368-531 (analysis), :740-856 (synthesis); matmul_transform_3.py:131-300, :303-480
+# the 1-D level operator is applied along every axis as a dense matmul
+# ---------------------------------------------------------------------------------------------
+def _apply_along(mat: torch.Tensor, x: torch.Tensor, dim: int) -> torch.Tensor:
+    return torch.movedim(torch.tensordot(mat, x, dims=([1], [dim])), 0, dim)
+
+
+def _odd_pad_axis(x: torch.Tensor, dim: int, mode: str) -> torch.Tensor:
+    moved = torch.movedim(x, dim, -1)
+    flat = moved.reshape(-1, moved.shape[-1])
+    return torch.movedim(_odd_pad(flat, mode).reshape(*moved.shape[:-1], moved.shape[-1] + 1), -1, dim)
+
+
+_KEYS_ND = {2: ("ad", "da", "dd"), 3: ("aad", "ada", "add", "daa", "dad", "dda", "ddd")}
+
+
+class _MatrixWavedecNd:
+    ndim = 2
+
+    def __init__(self, wavelet, level=None, *, axes=None, orthogonalization="qr", odd_coeff_padding_mode="zero"):
+        self.wavelet = as_wavelet(wavelet)
+        self.level = level
+        self.axes = _axes(axes, self.ndim)
+        self.method = orthogonalization
+        self.odd_mode = odd_coeff_padding_mode
+
+    def __call__(self, data):
+        nd = self.ndim
+        x, shape = _fold(data, nd, self.axes)
+        dec_lo, dec_hi, _, _ = _taps(self.wavelet, x.dtype, flip=False)
+        L = dec_lo.shape[0]
+        if self.level is None:
+            self.level = int(np.min([np.log2(s / (L - 1)) for s in x.shape[1:]]))
+        elif self.level <= 0:
+            raise ValueError("level must be a positive integer.")
+        cur = x
+        out = []
+        for _ in range(self.level):
+            if any(s < L for s in cur.shape[1:]):
+                break
+            for a in range(nd, 0, -1):
+                if cur.shape[a] % 2:
+                    cur = _odd_pad_axis(cur, a, self.odd_mode)
+            for a in range(nd, 0, -1):
+                cur = _apply_along(boundary_matrix(dec_lo, dec_hi, cur.shape[a], self.method), cur, a)
+            half = [s // 2 for s in cur.shape[1:]]
+            bands = {}
+            for key in _KEYS_ND[nd]:
+                sl = tuple(slice(half[a], None) if key[a] == "d" else slice(0, half[a]) for a in range(nd))
+                bands[key] = cur[(slice(None),) + sl]
+            out.append(bands)
+            cur = cur[(slice(None),) + tuple(slice(0, h) for h in half)]
+        res = [_unfold(cur, nd, self.axes, shape)]
+        for bands in reversed(out):
+            un = {k: _unfold(v, nd, self.axes, shape) for k, v in bands.items()}
+            res.append((un["ad"], un["da"], un["dd"]) if nd == 2 else un)
+        return tuple(res)
+
+
+class MatrixWavedec2(_MatrixWavedecNd):
+    ndim = 2
+
+    def __init__(self, wavelet, level=None, *, axes=None, orthogonalization="qr", separable=True,
+                 odd_coeff_padding_mode="zero"):
+        if not separable:
+            raise NotImplementedError("port covers the separable operator only")
+        super().__init__(wavelet, level, axes=axes, orthogonalization=orthogonalization,
+                         odd_coeff_padding_mode=odd_coeff_padding_mode)
+
+
+class MatrixWavedec3(_MatrixWavedecNd):
+    ndim = 3
+
+
+class _MatrixWaverecNd:
+    ndim = 2
+
+    def __init__(self, wavelet, *, axes=None, orthogonalization="qr", separable=True):
+        if not separable:
+            raise NotImplementedError("port covers the separable operator only")
+        self.wavelet = as_wavelet(wavelet)
+        self.axes = _axes(axes, self.ndim)
+        self.method = orthogonalization
+
+    def __call__(self, coeffs):
+        nd = self.ndim
+        lead, shape = _fold(coeffs[0], nd, self.axes)
+        _, _, rec_lo, rec_hi = _taps(self.wavelet, lead.dtype, flip=True)
+        cur = lead
+        for el in coeffs[1:]:
+            if nd == 2:
+                el = {"ad": el[0], "da": el[1], "dd": el[2]}
+            bands = {k: _fold(v, nd, self.axes, len(shape))[0] for k, v in el.items()}
+            dshape = tuple(bands["d" * nd].shape[1:])
+            full = torch.zeros((cur.shape[0],) + tuple(2 * c for c in dshape), dtype=cur.dtype)
+            full[(slice(None),) + tuple(slice(0, c) for c in dshape)] = cur[(slice(None),) + tuple(slice(0, c) for c in dshape)]
+            for key, t in bands.items():
+                sl = tuple(slice(dshape[a], None) if key[a] == "d" else slice(0, dshape[a]) for a in range(nd))
+                full[(slice(None),) + sl] = t
+            cur = full
+            for a in range(nd, 0, -1):
+                cur = _apply_along(boundary_matrix(rec_lo, rec_hi, cur.shape[a], self.method).T, cur, a)
+        return _unfold(cur, nd, self.axes, shape)
+
+
+class MatrixWaverec2(_MatrixWaverecNd):
+    ndim = 2
+
+
+class MatrixWaverec3(_MatrixWaverecNd):
+    ndim = 3
+
+    def __init__(self, wavelet, *, axes=None, orthogonalization="qr"):
+        super().__init__(wavelet, axes=axes, orthogonalization=orthogonalization)

@@ -23,6 +23,7 @@ from .constants import (
 )
 from .fwt import wavedec, wavedec2, wavedec3, waverec, waverec2, waverec3
 from .matrix_fwt import MatrixWavedec, MatrixWaverec, construct_boundary_a, construct_boundary_s
+from .matrix_fwt_nd import MatrixWavedec2, MatrixWavedec3, MatrixWaverec2, MatrixWaverec3
 from .separable import fswavedec2, fswavedec3, fswaverec2, fswaverec3
 
 __version__ = "0.1.0"
@@ -31,7 +32,10 @@ HOT_PATH_NAMES = (
     "wavedec", "waverec", "wavedec2", "waverec2", "wavedec3", "waverec3", "MatrixWavedec", "MatrixWaverec",
 )
 #: "next" rows of SURVEY.md section 8(f) that ride on the same kernels
-NEXT_ROW_NAMES = ("fswavedec2", "fswavedec3", "fswaverec2", "fswaverec3")
+NEXT_ROW_NAMES = (
+    "fswavedec2", "fswavedec3", "fswaverec2", "fswaverec3",
+    "MatrixWavedec2", "MatrixWaverec2", "MatrixWavedec3", "MatrixWaverec3",  # separable mode only
+)
 
 __all__ = list(HOT_PATH_NAMES) + list(NEXT_ROW_NAMES) + [
     "Wavelet", "WaveletTensorTuple", "WaveletDetailTuple2d", "WaveletDetailDict", "WaveletCoeff1d",

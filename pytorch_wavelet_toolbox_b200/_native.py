@@ -58,6 +58,10 @@ SIGNATURES = {
     "wt_matrix_inv": (C.c_int, [C.c_int, C.c_int, C.c_int, _f64p, _f64p, _i64p, _i64p, _i32p, _i32p, _i32p,
                                 _i32p, _vp, _vp, _i64, C.POINTER(_vp), _i64p, _i64, _vp, _i64, _vp, C.c_size_t,
                                 C.c_int, _vp]),
+    "wt_matrix_axis_fwd": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
+    "wt_matrix_axis_inv": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "wt_launch_count": (C.c_uint64, []),
     "wt_launch_count_reset": (None, []),
 }

@@ -275,4 +275,118 @@ static bool launch_mat_inv_fast(const MatInvParams<T>& p, cudaStream_t st, cudaE
     return true;
 }
 
+// ------------------------------------------------------------------------------------------
+// One level of the operator along an arbitrary axis of a [outer, n, inner] tensor (inner contiguous):
+// the separable 2-D / 3-D boundary-wavelet transforms apply the 1-D operator along each axis
+// (reference src/ptwt/matmul_transform_2.py:514-531, matmul_transform_3.py:255-262).  Consecutive
+// threads walk the contiguous inner index, so every access is coalesced whatever the axis.
+// Output layout = the reference's "A x, then split": low-pass rows 0 .. n/2-1, high-pass n/2 .. n-1
+// along the transformed axis of one [outer, n, inner] buffer.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct MatAxisParams {
+    const T* x;       // analysis: [outer, n_in, inner]; synthesis: [outer, n, inner] (lo | hi along the axis)
+    T* y;             // analysis: [outer, n, inner] (lo | hi);  synthesis: [outer, keep, inner]
+    int64_t outer, inner, n, n_in, keep;
+    int64_t x_os, x_as, y_os, y_as;   // outer / axis strides in elements
+    int L, shift, odd_mode;
+    int nb_top, nb_bot, w_left, w_right;
+    const T* lo_left;
+    const T* lo_right;
+    const T* hi_left;
+    const T* hi_right;
+    Taps<T> taps;
+};
+
+template <typename T>
+__device__ __forceinline__ T mat_axis_sample(const T* __restrict__ xc, int64_t s, int64_t as, int64_t n_in, int odd_mode) {
+    if (s < n_in) return __ldg(xc + s * as);
+    switch (odd_mode) {   // the single appended sample of an odd extent (F.pad(..., (0, 1)) along this axis)
+        case WT_MODE_ZERO: return T(0);
+        case WT_MODE_REFLECT: return __ldg(xc + (n_in >= 2 ? n_in - 2 : 0) * as);
+        case WT_MODE_PERIODIC: return __ldg(xc);
+        default: return __ldg(xc + (n_in - 1) * as);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) mat_axis_fwd_kernel(const __grid_constant__ MatAxisParams<T> p) {
+    const int64_t half = p.n / 2;
+    const int64_t total = p.outer * half * p.inner;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx % p.inner;
+        const int64_t r = idx / p.inner;
+        const int64_t i = r % half, o = r / half;
+        const T* __restrict__ xc = p.x + o * p.x_os + c;
+        T alo = T(0), ahi = T(0);
+        if (i < p.nb_top || i >= half - p.nb_bot) {
+            const int64_t rr = i < p.nb_top ? i : p.nb_top + (i - (half - p.nb_bot));
+            for (int q = 0; q < p.w_left; ++q) {
+                const T v = mat_axis_sample(xc, (int64_t)q, p.x_as, p.n_in, p.odd_mode);
+                alo = fma(__ldg(p.lo_left + rr * p.w_left + q), v, alo);
+                ahi = fma(__ldg(p.hi_left + rr * p.w_left + q), v, ahi);
+            }
+            const int64_t c0 = p.n - p.w_right;
+            for (int q = 0; q < p.w_right; ++q) {
+                const T v = mat_axis_sample(xc, c0 + q, p.x_as, p.n_in, p.odd_mode);
+                alo = fma(__ldg(p.lo_right + rr * p.w_right + q), v, alo);
+                ahi = fma(__ldg(p.hi_right + rr * p.w_right + q), v, ahi);
+            }
+        } else {
+            const int64_t top = 2 * i + p.shift;
+            for (int m = 0; m < p.L; ++m) {
+                const int64_t s = top - m;
+                if (s < 0 || s >= p.n) continue;
+                const T v = mat_axis_sample(xc, s, p.x_as, p.n_in, p.odd_mode);
+                alo = fma(p.taps.lo[m], v, alo);
+                ahi = fma(p.taps.hi[m], v, ahi);
+            }
+        }
+        T* __restrict__ yc = p.y + o * p.y_os + c;
+        yc[i * p.y_as] = alo;
+        yc[(half + i) * p.y_as] = ahi;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) mat_axis_inv_kernel(const __grid_constant__ MatAxisParams<T> p) {
+    const int64_t half = p.n / 2;
+    const int64_t total = p.outer * p.keep * p.inner;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = idx % p.inner;
+        const int64_t r = idx / p.inner;
+        const int64_t t = r % p.keep, o = r / p.keep;
+        const T* __restrict__ lc = p.x + o * p.x_os + c;          // low-pass rows
+        const T* __restrict__ hc = lc + half * p.x_as;            // high-pass rows
+        T acc = T(0);
+        int64_t i0 = (t - p.shift + 1) >> 1;
+        int64_t i1 = (t - p.shift + p.L - 1) >> 1;
+        if (i0 < p.nb_top) i0 = p.nb_top;
+        if (i1 > half - p.nb_bot - 1) i1 = half - p.nb_bot - 1;
+        for (int64_t i = i0; i <= i1; ++i) {
+            const int m = (int)(2 * i + p.shift - t);
+            acc = fma(p.taps.lo[m], __ldg(lc + i * p.x_as), acc);
+            acc = fma(p.taps.hi[m], __ldg(hc + i * p.x_as), acc);
+        }
+        const int nb = p.nb_top + p.nb_bot;
+        if (t < p.w_left) {
+            for (int rr = 0; rr < nb; ++rr) {
+                const int64_t i = rr < p.nb_top ? rr : half - p.nb_bot + (rr - p.nb_top);
+                acc = fma(__ldg(p.lo_left + rr * p.w_left + t), __ldg(lc + i * p.x_as), acc);
+                acc = fma(__ldg(p.hi_left + rr * p.w_left + t), __ldg(hc + i * p.x_as), acc);
+            }
+        }
+        const int64_t c0 = p.n - p.w_right;
+        if (t >= c0) {
+            const int64_t q = t - c0;
+            for (int rr = 0; rr < nb; ++rr) {
+                const int64_t i = rr < p.nb_top ? rr : half - p.nb_bot + (rr - p.nb_top);
+                acc = fma(__ldg(p.lo_right + rr * p.w_right + q), __ldg(lc + i * p.x_as), acc);
+                acc = fma(__ldg(p.hi_right + rr * p.w_right + q), __ldg(hc + i * p.x_as), acc);
+            }
+        }
+        p.y[o * p.y_os + t * p.y_as + c] = acc;
+    }
+}
+
 }  // namespace wtb

@@ -671,6 +671,82 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
 
 using namespace wtb;
 
+template <typename T>
+static int matrix_axis_t(bool inverse, int L, const double* flo, const double* fhi, int64_t n, int64_t n_in, int64_t keep,
+                         int odd_mode, int nbt, int nbb, int wl, int wr, const void* blocks, const void* x, int64_t outer,
+                         int64_t inner, int64_t xos, int64_t xas, void* y, int64_t yos, int64_t yas, cudaStream_t st) {
+    MatAxisParams<T> p;
+    fill_taps(p.taps, flo, fhi, L, inverse);  // synthesis: rows of S^T carry the flipped rec filters
+    p.x = (const T*)x; p.y = (T*)y;
+    p.outer = outer; p.inner = inner; p.n = n; p.n_in = n_in; p.keep = keep;
+    p.x_os = xos; p.x_as = xas; p.y_os = yos; p.y_as = yas;
+    p.L = L; p.shift = L / 2 + (L % 2); p.odd_mode = odd_mode;
+    p.nb_top = nbt; p.nb_bot = nbb; p.w_left = wl; p.w_right = wr;
+    const T* blk = (const T*)blocks;
+    const int64_t nb = (int64_t)nbt + nbb;
+    p.lo_left = blk; blk += nb * wl;
+    p.lo_right = blk; blk += nb * wr;
+    p.hi_left = blk; blk += nb * wl;
+    p.hi_right = blk;
+    const int64_t total = outer * (inverse ? keep : n / 2) * inner;
+    if (total <= 0) return 0;
+    // contiguous axis: the register-blocked 1-D kernels of MatrixWavedec / MatrixWaverec apply directly
+    if (inner == 1 && xas == 1 && yas == 1 && n < (int64_t(1) << 30) && !(L & 1) && L <= 16 && !getenv("WTB200_DISABLE_FUSED")) {
+        cudaError_t e = cudaSuccess;
+        bool done = true;
+        // the row index rides on gridDim.y: at most 65535 rows per launch
+        for (int64_t r0 = 0; r0 < outer && done && e == cudaSuccess; r0 += 65535) {
+            const int64_t rows = outer - r0 < 65535 ? outer - r0 : 65535;
+            if (inverse) {
+                MatInvParams<T> q;
+                q.lo = p.x + r0 * xos; q.hi = q.lo + n / 2; q.y = p.y + r0 * yos;
+                q.batch = rows; q.n = n; q.keep = keep; q.lo_stride = xos; q.hi_stride = xos; q.y_stride = yos;
+                q.L = L; q.shift = p.shift;
+                q.nb_top = nbt; q.nb_bot = nbb; q.w_left = wl; q.w_right = wr;
+                q.lo_left = p.lo_left; q.lo_right = p.lo_right; q.hi_left = p.hi_left; q.hi_right = p.hi_right;
+                q.taps = p.taps;
+                done = launch_mat_inv_fast<T>(q, st, &e);
+            } else {
+                Fast1dParams<T> fp;
+                memset(&fp, 0, sizeof(fp));
+                fp.x = p.x + r0 * xos; fp.lo = p.y + r0 * yos; fp.hi = fp.lo + n / 2;
+                fp.xs = xos; fp.ls = yos; fp.hs = yos;
+                fp.n = (int)n; fp.n_in = (int)n_in; fp.m = (int)(n / 2);
+                fp.base = p.shift - (L - 1); fp.mode = odd_mode;
+                fp.nb_top = nbt; fp.nb_bot = nbb; fp.w_left = wl; fp.w_right = wr;
+                fp.lo_left = p.lo_left; fp.lo_right = p.lo_right; fp.hi_left = p.hi_left; fp.hi_right = p.hi_right;
+                for (int k = 0; k < L; ++k) { fp.flo[k] = p.taps.lo[L - 1 - k]; fp.fhi[k] = p.taps.hi[L - 1 - k]; }
+                done = launch_axis1d_fast<T, true>(fp, L, rows, st, &e);
+            }
+            if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
+            else if (r0 > 0) return fail(WT_EUNSUPPORTED, "row chunk %lld rejected by the fast path", (long long)r0);
+        }
+        if (done) {
+            if (e != cudaSuccess) return cuda_fail(e, inverse ? "mat_inv_fast_kernel" : "axis1d_fast_kernel");
+            return 0;
+        }
+    }
+    if (inverse) mat_axis_inv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+    else mat_axis_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, inverse ? "mat_axis_inv_kernel" : "mat_axis_fwd_kernel");
+    return 0;
+}
+
+static int matrix_axis_check(int dtype, int filt_len, const double* lo, const double* hi, int64_t n, int nbt, int nbb, int wl,
+                             int wr, const void* blocks, const void* x, const void* y, int64_t outer, int64_t inner) {
+    if (dtype != WT_F32 && dtype != WT_F64) return fail(WT_EINVAL, "dtype must be WT_F32 or WT_F64");
+    if (filt_len < 2 || filt_len > WT_MAX_FILT_LEN) return fail(WT_EUNSUPPORTED, "filter length %d", filt_len);
+    if (!lo || !hi) return fail(WT_EINVAL, "NULL filter");
+    if (n < 2 || (n & 1)) return fail(WT_ESHAPE, "operator size %lld must be even", (long long)n);
+    if (outer < 0 || inner < 0) return fail(WT_EINVAL, "negative extent");
+    if (nbt < 0 || nbb < 0 || wl < 0 || wr < 0 || (int64_t)nbt + nbb > n / 2 || wl > n || wr > n)
+        return fail(WT_EINVAL, "boundary block geometry");
+    if (outer * inner > 0 && (!x || !y || (!blocks && nbt + nbb > 0))) return fail(WT_EINVAL, "NULL argument");
+    return 0;
+}
+
 extern "C" {
 
 int wt_version(void) { return WT_VERSION; }
@@ -788,6 +864,38 @@ int wt_matrix_inv(int dtype, int levels, int filt_len, const double* rec_lo, con
     return matrix_inv_t<double>(levels, filt_len, rec_lo, rec_hi, n, next_len, nb_top, nb_bot, w_left, w_right,
                                 blocks, lo_in, lo_stride, hi_in, hi_stride, batch, y, y_stride, scratch,
                                 scratch_bytes, allow_fused, st);
+}
+
+int wt_matrix_axis_fwd(int dtype, int filt_len, const double* dec_lo, const double* dec_hi, int64_t n, int padded,
+                       int odd_mode, int nb_top, int nb_bot, int w_left, int w_right, const void* blocks, const void* x,
+                       int64_t outer, int64_t inner, int64_t x_outer_stride, int64_t x_axis_stride, void* y,
+                       int64_t y_outer_stride, int64_t y_axis_stride, void* stream) {
+    int rc = matrix_axis_check(dtype, filt_len, dec_lo, dec_hi, n, nb_top, nb_bot, w_left, w_right, blocks, x, y, outer, inner);
+    if (rc) return rc;
+    if (odd_mode < WT_MODE_ZERO || odd_mode > WT_MODE_SYMMETRIC) return fail(WT_EINVAL, "padding mode %d", odd_mode);
+    const int64_t n_in = n - (padded ? 1 : 0);
+    if (n_in < 1) return fail(WT_ESHAPE, "empty axis");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WT_F32)
+        return matrix_axis_t<float>(false, filt_len, dec_lo, dec_hi, n, n_in, n, odd_mode, nb_top, nb_bot, w_left, w_right, blocks,
+                                    x, outer, inner, x_outer_stride, x_axis_stride, y, y_outer_stride, y_axis_stride, st);
+    return matrix_axis_t<double>(false, filt_len, dec_lo, dec_hi, n, n_in, n, odd_mode, nb_top, nb_bot, w_left, w_right, blocks,
+                                 x, outer, inner, x_outer_stride, x_axis_stride, y, y_outer_stride, y_axis_stride, st);
+}
+
+int wt_matrix_axis_inv(int dtype, int filt_len, const double* rec_lo, const double* rec_hi, int64_t n, int64_t keep,
+                       int nb_top, int nb_bot, int w_left, int w_right, const void* blocks, const void* x, int64_t outer,
+                       int64_t inner, int64_t x_outer_stride, int64_t x_axis_stride, void* y, int64_t y_outer_stride,
+                       int64_t y_axis_stride, void* stream) {
+    int rc = matrix_axis_check(dtype, filt_len, rec_lo, rec_hi, n, nb_top, nb_bot, w_left, w_right, blocks, x, y, outer, inner);
+    if (rc) return rc;
+    if (keep < 0 || keep > n) return fail(WT_ESHAPE, "keep %lld of %lld samples", (long long)keep, (long long)n);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == WT_F32)
+        return matrix_axis_t<float>(true, filt_len, rec_lo, rec_hi, n, n, keep, WT_MODE_ZERO, nb_top, nb_bot, w_left, w_right, blocks,
+                                    x, outer, inner, x_outer_stride, x_axis_stride, y, y_outer_stride, y_axis_stride, st);
+    return matrix_axis_t<double>(true, filt_len, rec_lo, rec_hi, n, n, keep, WT_MODE_ZERO, nb_top, nb_bot, w_left, w_right, blocks,
+                                 x, outer, inner, x_outer_stride, x_axis_stride, y, y_outer_stride, y_axis_stride, st);
 }
 
 uint64_t wt_launch_count(void) { return g_launches.load(); }

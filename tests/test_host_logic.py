@@ -193,3 +193,30 @@ def test_install_is_a_noop_without_ptwt():
     if importlib.util.find_spec("ptwt") is None:
         with pytest.raises(ModuleNotFoundError):
             wt.install()
+
+
+def test_separable_matrix_nd_argument_errors():
+    """MatrixWavedec2/3 mirror the reference's constructor checks (matmul_transform_2.py:329-341,
+    matmul_transform_3.py:121-128); the non-separable operator is declared out of scope."""
+    import pytorch_wavelet_toolbox_b200 as wt
+
+    with pytest.raises(NotImplementedError):
+        wt.MatrixWavedec2("haar", 2, orthogonalization="cholesky")
+    with pytest.raises(NotImplementedError):
+        wt.MatrixWavedec3("haar", 2, orthogonalization="cholesky")
+    with pytest.raises(ValueError):
+        wt.MatrixWavedec2("haar", 2, axes=(1, 1))
+    with pytest.raises(ValueError):
+        wt.MatrixWaverec3("haar", axes=(0, 1))
+    with pytest.raises(NotImplementedError):
+        wt.MatrixWavedec2("haar", 2, separable=False)(torch.zeros(2, 8, 8))
+    with pytest.raises(NotImplementedError):
+        wt.MatrixWavedec2("haar", 2).sparse_fwt_operator
+    with pytest.raises(ValueError):
+        wt.MatrixWavedec2("haar", 0)(torch.zeros(2, 8, 8))
+    with pytest.raises(ValueError):
+        wt.MatrixWaverec2("haar")((torch.zeros(2, 4, 4), [torch.zeros(2, 4, 4)] * 3))
+    with pytest.raises(ValueError):
+        wt.MatrixWaverec3("haar")((torch.zeros(2, 4, 4, 4), (torch.zeros(2, 4, 4, 4),)))
+    with pytest.warns(DeprecationWarning):
+        wt.MatrixWavedec2("haar", 2, boundary="qr")

@@ -30,6 +30,11 @@ def _run_port(case, x):
         kw = {} if axes is None else {"axes": axes}
         c = P.wavedec3(x, wav, mode=mode, level=level, **kw)
         return c, P.waverec3(c, wav, **kw)
+    if fam in ("matrix2", "matrix3"):
+        kw = {} if axes is None else {"axes": axes}
+        dec, rec = ((P.MatrixWavedec2, P.MatrixWaverec2) if fam == "matrix2" else (P.MatrixWavedec3, P.MatrixWaverec3))
+        c = dec(wav, level, odd_coeff_padding_mode=mode, **kw)(x)
+        return c, rec(wav, **kw)(c)
     meth = "gramschmidt" if fam == "matrix_gs" else "qr"
     c = P.MatrixWavedec(wav, level, orthogonalization=meth, odd_coeff_padding_mode=mode)(x)
     return c, P.MatrixWaverec(wav, orthogonalization=meth)(c)

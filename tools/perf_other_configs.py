@@ -72,6 +72,14 @@ if "mat" in which:
     inv = wt.MatrixWaverec("db6")
     ms, r, host, gr = timeit(lambda: inv(c))
     report("MatrixWaverec of it", (ms, host, gr), nbytes(r) + nbytes(c))
+if "mat2" in which:
+    x = torch.randn(32, 2048, 2048, device="cuda")
+    fw2 = wt.MatrixWavedec2("db4", 4)
+    ms, c, host, gr = timeit(lambda: fw2(x))
+    report("MatrixWavedec2 db4 L4 32x2048^2 f32 (separable, 8f row 2)", (ms, host, gr), 2 * nbytes(x))
+    inv2 = wt.MatrixWaverec2("db4")
+    ms, r, host, gr = timeit(lambda: inv2(c))
+    report("MatrixWaverec2 of it", (ms, host, gr), 2 * nbytes(x))
 if "db8" in which:
     x = torch.randn(128, 2048, 2048, device="cuda")
     ms, c, host, gr = timeit(lambda: wt.wavedec2(x, "db8", level=5))
