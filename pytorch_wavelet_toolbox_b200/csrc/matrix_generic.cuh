@@ -389,4 +389,174 @@ __global__ void __launch_bounds__(256) mat_axis_inv_kernel(const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Register-blocked versions of the two per-axis kernels for a STRIDED axis (inner > 1): a thread owns one
+// column c of the inner index and R = 4 consecutive outputs along the axis, loads the 2 R + L - 2 samples
+// (analysis) or the window of both bands (synthesis) it needs once -- every load is a coalesced row
+// segment across the warp -- and applies the taps with compile-time indices.  Groups that touch an
+// orthogonalised boundary row, a corner block or the appended odd sample fall back to the per-output
+// evaluation of the kernels above.  blockDim = (64 columns, 4 groups); grid.z strides over `outer`.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void mat_axis_fwd_one(const MatAxisParams<T>& p, const T* __restrict__ xc, int64_t i, T& alo, T& ahi) {
+    const int64_t half = p.n / 2;
+    alo = T(0); ahi = T(0);
+    if (i < p.nb_top || i >= half - p.nb_bot) {
+        const int64_t rr = i < p.nb_top ? i : p.nb_top + (i - (half - p.nb_bot));
+        for (int q = 0; q < p.w_left; ++q) {
+            const T v = mat_axis_sample(xc, (int64_t)q, p.x_as, p.n_in, p.odd_mode);
+            alo = fma(__ldg(p.lo_left + rr * p.w_left + q), v, alo);
+            ahi = fma(__ldg(p.hi_left + rr * p.w_left + q), v, ahi);
+        }
+        const int64_t c0 = p.n - p.w_right;
+        for (int q = 0; q < p.w_right; ++q) {
+            const T v = mat_axis_sample(xc, c0 + q, p.x_as, p.n_in, p.odd_mode);
+            alo = fma(__ldg(p.lo_right + rr * p.w_right + q), v, alo);
+            ahi = fma(__ldg(p.hi_right + rr * p.w_right + q), v, ahi);
+        }
+    } else {
+        const int64_t top = 2 * i + p.shift;
+        for (int m = 0; m < p.L; ++m) {
+            const int64_t s = top - m;
+            if (s < 0 || s >= p.n) continue;
+            const T v = mat_axis_sample(xc, s, p.x_as, p.n_in, p.odd_mode);
+            alo = fma(p.taps.lo[m], v, alo);
+            ahi = fma(p.taps.hi[m], v, ahi);
+        }
+    }
+}
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256) mat_axis_fwd_blk_kernel(const __grid_constant__ MatAxisParams<T> p) {
+    constexpr int R = 4, NS = 2 * R + L - 2;
+    const int64_t c = (int64_t)blockIdx.x * 64 + threadIdx.x;
+    const int64_t half = p.n / 2;
+    const int64_t i0 = ((int64_t)blockIdx.y * 4 + threadIdx.y) * R;
+    if (c >= p.inner || i0 >= half) return;
+    const int shift = L / 2;
+    const int64_t s0 = 2 * i0 + shift - (L - 1);                 // first sample of the group's window
+    const bool fast = i0 >= p.nb_top && i0 + R <= half - p.nb_bot && s0 >= 0 && s0 + NS <= p.n_in;
+    for (int64_t o = blockIdx.z; o < p.outer; o += gridDim.z) {
+        const T* __restrict__ xc = p.x + o * p.x_os + c;
+        T* __restrict__ yc = p.y + o * p.y_os + c;
+        if (fast) {
+            T v[NS];
+#pragma unroll
+            for (int q = 0; q < NS; ++q) v[q] = __ldg(xc + (s0 + q) * p.x_as);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                T alo = T(0), ahi = T(0);
+#pragma unroll
+                for (int m = 0; m < L; ++m) {
+                    alo = fma(p.taps.lo[m], v[2 * r + (L - 1) - m], alo);
+                    ahi = fma(p.taps.hi[m], v[2 * r + (L - 1) - m], ahi);
+                }
+                yc[(i0 + r) * p.y_as] = alo;
+                yc[(half + i0 + r) * p.y_as] = ahi;
+            }
+        } else {
+            for (int r = 0; r < R && i0 + r < half; ++r) {
+                T alo, ahi;
+                mat_axis_fwd_one(p, xc, i0 + r, alo, ahi);
+                yc[(i0 + r) * p.y_as] = alo;
+                yc[(half + i0 + r) * p.y_as] = ahi;
+            }
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ T mat_axis_inv_one(const MatAxisParams<T>& p, const T* __restrict__ lc, const T* __restrict__ hc, int64_t t) {
+    const int64_t half = p.n / 2;
+    T acc = T(0);
+    int64_t i0 = (t - p.shift + 1) >> 1;
+    int64_t i1 = (t - p.shift + p.L - 1) >> 1;
+    if (i0 < p.nb_top) i0 = p.nb_top;
+    if (i1 > half - p.nb_bot - 1) i1 = half - p.nb_bot - 1;
+    for (int64_t i = i0; i <= i1; ++i) {
+        const int m = (int)(2 * i + p.shift - t);
+        acc = fma(p.taps.lo[m], __ldg(lc + i * p.x_as), acc);
+        acc = fma(p.taps.hi[m], __ldg(hc + i * p.x_as), acc);
+    }
+    const int nb = p.nb_top + p.nb_bot;
+    if (t < p.w_left) {
+        for (int rr = 0; rr < nb; ++rr) {
+            const int64_t i = rr < p.nb_top ? rr : half - p.nb_bot + (rr - p.nb_top);
+            acc = fma(__ldg(p.lo_left + rr * p.w_left + t), __ldg(lc + i * p.x_as), acc);
+            acc = fma(__ldg(p.hi_left + rr * p.w_left + t), __ldg(hc + i * p.x_as), acc);
+        }
+    }
+    const int64_t c0 = p.n - p.w_right;
+    if (t >= c0) {
+        const int64_t q = t - c0;
+        for (int rr = 0; rr < nb; ++rr) {
+            const int64_t i = rr < p.nb_top ? rr : half - p.nb_bot + (rr - p.nb_top);
+            acc = fma(__ldg(p.lo_right + rr * p.w_right + q), __ldg(lc + i * p.x_as), acc);
+            acc = fma(__ldg(p.hi_right + rr * p.w_right + q), __ldg(hc + i * p.x_as), acc);
+        }
+    }
+    return acc;
+}
+
+template <typename T, int L>
+__global__ void __launch_bounds__(256) mat_axis_inv_blk_kernel(const __grid_constant__ MatAxisParams<T> p) {
+    constexpr int R = 4, H = L / 2, C = L / 4;
+    constexpr int NCW = C + (R + H - 2) / 2 + 1;                  // coefficients per band in the window of R samples
+    const int64_t c = (int64_t)blockIdx.x * 64 + threadIdx.x;
+    const int64_t half = p.n / 2;
+    const int64_t t0 = ((int64_t)blockIdx.y * 4 + threadIdx.y) * R;
+    if (c >= p.inner || t0 >= p.keep) return;
+    const int64_t ilo = t0 / 2 - C;
+    const bool fast = ilo >= p.nb_top && ilo + NCW <= half - p.nb_bot && t0 >= p.w_left && t0 + R <= p.n - p.w_right &&
+                      t0 + R <= p.keep;
+    for (int64_t o = blockIdx.z; o < p.outer; o += gridDim.z) {
+        const T* __restrict__ lc = p.x + o * p.x_os + c;
+        const T* __restrict__ hc = lc + half * p.x_as;
+        T* __restrict__ yc = p.y + o * p.y_os + c;
+        if (fast) {
+            T a[NCW], d[NCW];
+#pragma unroll
+            for (int w = 0; w < NCW; ++w) { a[w] = __ldg(lc + (ilo + w) * p.x_as); d[w] = __ldg(hc + (ilo + w) * p.x_as); }
+#pragma unroll
+            for (int e = 0; e < R; ++e) {
+                T acc = T(0);
+#pragma unroll
+                for (int w = 0; w < NCW; ++w) {
+                    const int kk = e + H - 1 + 2 * C - 2 * w;     // rec index; the taps are stored flipped
+                    if (kk >= 0 && kk < L) {
+                        acc = fma(p.taps.lo[L - 1 - kk], a[w], acc);
+                        acc = fma(p.taps.hi[L - 1 - kk], d[w], acc);
+                    }
+                }
+                yc[(t0 + e) * p.y_as] = acc;
+            }
+        } else {
+            for (int e = 0; e < R && t0 + e < p.keep; ++e) yc[(t0 + e) * p.y_as] = mat_axis_inv_one(p, lc, hc, t0 + e);
+        }
+    }
+}
+
+template <typename T>
+static bool launch_mat_axis_blk(const MatAxisParams<T>& p, bool inverse, cudaStream_t st, cudaError_t* err) {
+    *err = cudaSuccess;
+    const int L = p.L;
+    if ((L & 1) || L < 2 || L > 16 || p.shift != L / 2 || p.inner < 2) return false;
+    const int64_t groups = ((inverse ? p.keep : p.n / 2) + 3) / 4;
+    const int64_t gx = (p.inner + 63) / 64, gy = (groups + 3) / 4;
+    if (gx > 0x7fffffff || gy > 65535) return false;
+    dim3 block(64, 4), grid((unsigned)gx, (unsigned)gy, (unsigned)(p.outer < 65535 ? p.outer : 65535));
+#define WTB_MAB(LL)                                                                   \
+    case LL:                                                                          \
+        if (inverse) mat_axis_inv_blk_kernel<T, LL><<<grid, block, 0, st>>>(p);       \
+        else mat_axis_fwd_blk_kernel<T, LL><<<grid, block, 0, st>>>(p);               \
+        break;
+    switch (L) {
+        WTB_MAB(2) WTB_MAB(4) WTB_MAB(6) WTB_MAB(8) WTB_MAB(10) WTB_MAB(12) WTB_MAB(14) WTB_MAB(16)
+        default: return false;
+    }
+#undef WTB_MAB
+    *err = cudaGetLastError();
+    return true;
+}
+
 }  // namespace wtb

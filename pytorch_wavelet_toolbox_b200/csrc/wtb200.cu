@@ -726,6 +726,14 @@ static int matrix_axis_t(bool inverse, int L, const double* flo, const double* f
             return 0;
         }
     }
+    if (inner > 1 && !getenv("WTB200_DISABLE_FUSED")) {
+        cudaError_t e = cudaSuccess;
+        if (launch_mat_axis_blk<T>(p, inverse, st, &e)) {
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            if (e != cudaSuccess) return cuda_fail(e, inverse ? "mat_axis_inv_blk_kernel" : "mat_axis_fwd_blk_kernel");
+            return 0;
+        }
+    }
     if (inverse) mat_axis_inv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
     else mat_axis_fwd_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
     g_launches.fetch_add(1, std::memory_order_relaxed);
