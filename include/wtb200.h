@@ -86,7 +86,12 @@ extern "C" {
  * floor((n_prev + L - 1) / 2) per axis (reference _get_pad, src/ptwt/_util.py:198-228).
  * detail bands k = 1 .. 2^ndim-1 live at  details + (k-1)*band_stride ;
  * the approximation band (k = 0) lives at `approx` (the returned cA for the coarsest
- * level, caller-provided scratch for the others). */
+ * level, caller-provided scratch for the others).
+ * SCRATCH SEMANTICS (analysis): the `approx` buffers of all but the coarsest level must hold
+ * `batch` items, but their contents are UNSPECIFIED on return -- the library processes the
+ * batch in chunks and reuses the first few item slots so that the intermediate approximations
+ * stay resident in L2 and never travel to HBM.  A caller that wants cA_l of an intermediate
+ * level runs a transform with `levels = l`. */
 typedef struct wt_level {
     void* details;
     void* approx;

@@ -764,39 +764,72 @@ static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* 
     *first_generic = 0;
     if (!fused2d_fwd_covers(ndim, L)) return 0;
     if (xs[1] != 1) return 0;
-    int nsplit = 1;
-    if (const char* ev = getenv("WTB200_SPLIT")) nsplit = atoi(ev);
-    else if (levels >= 2 && batch >= 16 && (int64_t)batch * dims[0] * dims[1] >= (int64_t(1) << 27)) nsplit = 2;
+    // Chunking: the batch is cut into chunks that alternate between the caller's stream and one auxiliary
+    // stream, so that the latency-bound deep levels of one chunk run under the bandwidth-bound level-1 launch
+    // of the next.  The intermediate approximations cA_1 .. cA_{n-1} are scratch, so every chunk reuses the
+    // scratch slots of its stream.  (Small chunks would keep those slots L2-resident -- tools/l2_hint_probe
+    // shows that a <= 32 MB buffer written, read and overwritten in place survives any amount of streaming
+    // traffic on B200 -- but with one launch per level and chunk the launch tails cost more than the saved
+    // traffic: 64 chunks 2.80 ms, 16 chunks 2.03 ms, 2 chunks 1.89 ms; tools/ab_chunk.sh.  The persistent
+    // kernel in fused2d_mega.cuh is the way to use that effect.)
+    int64_t chunk = 0;   // images per chunk
+    int nstreams = 2;
+    if (const char* ev = getenv("WTB200_CHUNK")) chunk = atoll(ev);
+    else if (levels >= 2 && batch >= 16 && (int64_t)batch * dims[0] * dims[1] >= (int64_t(1) << 27)) chunk = (batch + 1) / 2;
+    if (const char* ev = getenv("WTB200_STREAMS")) nstreams = atoi(ev) >= 2 ? 2 : 1;
+    if (const char* ev = getenv("WTB200_SPLIT")) {   // legacy knob: number of equal chunks, no scratch reuse change
+        const int ns = atoi(ev);
+        chunk = ns > 1 ? (batch + ns - 1) / ns : 0;
+    }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (nsplit > 1 && (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) nsplit = 1;
-    cudaStream_t s2 = nsplit > 1 ? aux_stream_for_current_device() : nullptr;
-    if (nsplit <= 1 || !s2 || levels > 32)
+    if (nstreams > 1 && (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) nstreams = 1;
+    cudaStream_t s2 = nstreams > 1 ? aux_stream_for_current_device() : nullptr;
+    if (!s2) nstreams = 1;
+    if (chunk <= 0 || chunk >= batch || levels > 32)
         return fused2d_fwd_run<T>(ndim, mode, levels, L, dlo, dhi, x, batch, dims, xs, xbs, lv, st, first_generic);
-    if (nsplit > batch) nsplit = (int)batch;
-    cudaEvent_t fork, join;
-    if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return cuda_fail(cudaGetLastError(), "event");
-    if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) { cudaEventDestroy(fork); return cuda_fail(cudaGetLastError(), "event"); }
-    cudaEventRecord(fork, st);
-    cudaStreamWaitEvent(s2, fork, 0);
+    cudaEvent_t fork = nullptr, join = nullptr;
+    if (nstreams > 1) {
+        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return cuda_fail(cudaGetLastError(), "event");
+        if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) { cudaEventDestroy(fork); return cuda_fail(cudaGetLastError(), "event"); }
+        cudaEventRecord(fork, st);
+        cudaStreamWaitEvent(s2, fork, 0);
+    }
     int rc = 0, fg = levels;
     wt_level sub[32];
-    for (int c = 0; c < nsplit && rc == 0; ++c) {
-        const int64_t b0 = batch * c / nsplit, b1 = batch * (c + 1) / nsplit;
-        if (b1 <= b0) continue;
+    int c = 0;
+    for (int64_t b0 = 0; b0 < batch && rc == 0; b0 += chunk, ++c) {
+        const int64_t b1 = b0 + chunk < batch ? b0 + chunk : batch;
+        const int which = nstreams > 1 ? (c & 1) : 0;
+        const int64_t slot0 = (int64_t)which * chunk;       // scratch slots of this stream (stream order protects reuse)
         for (int l = 0; l < levels; ++l) {
             sub[l] = lv[l];
             sub[l].details = (T*)lv[l].details + b0 * lv[l].details_batch_stride;
-            sub[l].approx = (T*)lv[l].approx + b0 * lv[l].approx_batch_stride;
+            // the last level's approximation is an output; the others are scratch (include/wtb200.h)
+            sub[l].approx = (T*)lv[l].approx + (l == levels - 1 ? b0 : slot0) * lv[l].approx_batch_stride;
         }
         int fgc = 0;
         rc = fused2d_fwd_run<T>(ndim, mode, levels, L, dlo, dhi, x + b0 * xbs, b1 - b0, dims, xs, xbs, sub,
-                                (c & 1) ? s2 : st, &fgc);
+                                which ? s2 : st, &fgc);
         if (fgc < fg) fg = fgc;
+        if (c == 0 && rc == 0 && fgc < levels && b1 < batch) {
+            // the fused kernels stop before the last level (the general path continues on the whole batch and
+            // needs every item's approximation in place): no scratch reuse -- do the rest in one plain call
+            for (int l = 0; l < levels; ++l) {
+                sub[l] = lv[l];
+                sub[l].details = (T*)lv[l].details + b1 * lv[l].details_batch_stride;
+                sub[l].approx = (T*)lv[l].approx + b1 * lv[l].approx_batch_stride;
+            }
+            rc = fused2d_fwd_run<T>(ndim, mode, levels, L, dlo, dhi, x + b1 * xbs, batch - b1, dims, xs, xbs, sub, st, &fgc);
+            if (fgc < fg) fg = fgc;
+            break;
+        }
     }
-    cudaEventRecord(join, s2);
-    cudaStreamWaitEvent(st, join, 0);
-    cudaEventDestroy(fork);
-    cudaEventDestroy(join);
+    if (nstreams > 1) {
+        cudaEventRecord(join, s2);
+        cudaStreamWaitEvent(st, join, 0);
+        cudaEventDestroy(fork);
+        cudaEventDestroy(join);
+    }
     *first_generic = fg;
     return rc;
 }

@@ -39,6 +39,7 @@ struct MegaLevel {
 struct MegaParams {
     MegaLevel lv[MEGA_MAXLEV];
     int levels, batch, mode;
+    int ring;                    // > 0: the intermediate approximations of image b live in scratch slot b % ring
     int items_per_period;        // sum over levels of nstrip * nseg
     int* counters;               // [0]: work queue; [1 + l * batch + b]: finished items of level l, image b
     float2 pl[8], ph[8], bl[16], bh[16];
@@ -133,16 +134,30 @@ fwd2d_mega_kernel(const __grid_constant__ MegaParams p, const __grid_constant__ 
         const MegaLevel& d = p.lv[l];
         const int sy = r / d.nstrip, sx = r - sy * d.nstrip;
 
-        // ---- wait for the producing level ----------------------------------------------------------
-        if (l > 0) {
+        // ---- wait for the producing level, and for the readers of the scratch slot this item overwrites ----
+        const bool writes_scratch = (l + 1 < p.levels);
+        const bool war = p.ring > 0 && writes_scratch && b >= p.ring;
+        if (l > 0 || war) {
             if (tid == 0) {
-                const int need = p.lv[l - 1].nstrip * p.lv[l - 1].nseg;
-                const int* cnt = p.counters + 1 + (l - 1) * p.batch + b;
-                while (ld_acquire(cnt) < need) __nanosleep(200);
+                if (l > 0) {
+                    const int need = p.lv[l - 1].nstrip * p.lv[l - 1].nseg;
+                    const int* cnt = p.counters + 1 + (l - 1) * p.batch + b;
+                    while (ld_acquire(cnt) < need) __nanosleep(200);
+                }
+                if (war) {
+                    // slot b % ring still holds cA_{l+1} of image b - ring until all its level-(l+1) items are done;
+                    // those items sit `ring - 1` periods earlier in the queue, so running CTAs hold them: no deadlock
+                    const int need = p.lv[l + 1].nstrip * p.lv[l + 1].nseg;
+                    const int* cnt = p.counters + 1 + (l + 1) * p.batch + (b - p.ring);
+                    while (ld_acquire(cnt) < need) __nanosleep(200);
+                }
                 asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy writes -> async-proxy (TMA) reads
             }
             __syncthreads();
         }
+        // batch index of the input / of the approximation output: scratch slots when the ring is on
+        const int b_in = (p.ring > 0 && l > 0) ? b % p.ring : b;
+        const int b_ap = (p.ring > 0 && writes_scratch) ? b % p.ring : b;
 
         // ---- one strip segment of level l (same algorithm as fwd2d_strip_f32_kernel) -----------------
         const int x0 = sx * TW;
@@ -160,14 +175,14 @@ fwd2d_mega_kernel(const __grid_constant__ MegaParams p, const __grid_constant__ 
                 for (int s = 0; s < 2 && s < nchunks; ++s) {
                     const uint32_t st = (gchunk + s) & 1;
                     mbar_expect_tx(&bars[st], (uint32_t)Gm::stage_bytes(4));
-                    if (HINTS) tma_load_3d_hint(s_in + st * IN_ROWS * SW, tm, &bars[st], c_in0, r_in0 + s * IN_ROWS, b, pol_first);
-                    else tma_load_3d(s_in + st * IN_ROWS * SW, tm, &bars[st], c_in0, r_in0 + s * IN_ROWS, b);
+                    if (HINTS) tma_load_3d_hint(s_in + st * IN_ROWS * SW, tm, &bars[st], c_in0, r_in0 + s * IN_ROWS, b_in, pol_first);
+                    else tma_load_3d(s_in + st * IN_ROWS * SW, tm, &bars[st], c_in0, r_in0 + s * IN_ROWS, b_in);
                 }
             }
-            const float* __restrict__ xb = d.x + (int64_t)b * d.x_bs;
+            const float* __restrict__ xb = d.x + (int64_t)b_in * d.x_bs;
             const int gx = x0 + 4 * cg;
             const bool col_ok = gx < d.Mw;
-            float* pL = d.out[half] + (int64_t)b * d.out_bs[half] + (int64_t)(yb + yl) * d.out_rs[half] + gx;
+            float* pL = d.out[half] + (int64_t)(half == 0 ? b_ap : b) * d.out_bs[half] + (int64_t)(yb + yl) * d.out_rs[half] + gx;
             float* pH = d.out[2 + half] + (int64_t)b * d.out_bs[2 + half] + (int64_t)(yb + yl) * d.out_rs[2 + half] + gx;
             const int64_t rsL = d.out_rs[half], rsH = d.out_rs[2 + half];
             // k = 0 is the approximation (re-read by the next level unless this is the last one)
@@ -236,8 +251,8 @@ fwd2d_mega_kernel(const __grid_constant__ MegaParams p, const __grid_constant__ 
                 if (tid == 0 && c + 2 < nchunks) {
                     fence_proxy_async();
                     mbar_expect_tx(&bars[stage], (uint32_t)Gm::stage_bytes(4));
-                    if (HINTS) tma_load_3d_hint(tile, tm, &bars[stage], c_in0, r_in0 + (c + 2) * IN_ROWS, b, pol_first);
-                    else tma_load_3d(tile, tm, &bars[stage], c_in0, r_in0 + (c + 2) * IN_ROWS, b);
+                    if (HINTS) tma_load_3d_hint(tile, tm, &bars[stage], c_in0, r_in0 + (c + 2) * IN_ROWS, b_in, pol_first);
+                    else tma_load_3d(tile, tm, &bars[stage], c_in0, r_in0 + (c + 2) * IN_ROWS, b_in);
                 }
                 // column pass
                 {
@@ -279,7 +294,7 @@ fwd2d_mega_kernel(const __grid_constant__ MegaParams p, const __grid_constant__ 
             }
         }
         // ---- publish ---------------------------------------------------------------------------------
-        if (l + 1 < p.levels) {
+        if (writes_scratch || p.ring > 0) {     // consumers wait on it; with the ring also the next writer of the slot
             __syncthreads();
             if (tid == 0) {
                 __threadfence();
@@ -334,7 +349,9 @@ static int launch_fwd2d_mega(int mode, int levels, const double* dlo, const doub
         for (int k = 0; k < 4; ++k)
             if (((uintptr_t)m.out[k] & 15) || (m.out_bs[k] & 3) || (m.out_rs[k] & 3) || m.out_rs[k] < (m.Mw + 3) / 4 * 4) m.vec_store = 0;
         constexpr int HH = Gm::HALO / 2;
-        int nseg = (m.Mh + 255) / 256;
+        int seg_target = 256;
+        if (const char* ev = getenv("WTB200_MEGA_SEG")) { const int v = atoi(ev); if (v >= 16 && v <= 4096) seg_target = v; }
+        int nseg = (m.Mh + seg_target - 1) / seg_target;
         int seg = ((m.Mh + nseg - 1) / nseg + HH + 15) / 16 * 16 - HH;
         if (seg < 16 - HH) seg = 16 - HH;
         nseg = (m.Mh + seg - 1) / seg;
@@ -345,6 +362,8 @@ static int launch_fwd2d_mega(int mode, int levels, const double* dlo, const doub
         H = m.Mh; W = m.Mw;
     }
     p.items_per_period = ipp;
+    p.ring = 0;
+    if (const char* ev = getenv("WTB200_MEGA_RING")) { const int v = atoi(ev); if (v >= 2 && v <= batch) p.ring = v; }
     if ((int64_t)ipp * (batch + levels) >= (int64_t(1) << 31)) return 0;
     float tl[16], th[16];
     for (int k = 0; k < L; ++k) { tl[k] = (float)dlo[k]; th[k] = (float)dhi[k]; }

@@ -519,10 +519,13 @@ def test_tiny_and_ragged_shapes():
     _cmp_tree(wt.wavedec3(v.to(DEV), "haar", level=1, mode="symmetric"), P.wavedec3(v, "haar", level=1, mode="symmetric"), "thin volume")
 
 
-def test_persistent_multilevel_kernel_when_enabled(monkeypatch):
+@pytest.mark.parametrize("ring", ["0", "2", "3"])
+def test_persistent_multilevel_kernel_when_enabled(monkeypatch, ring):
     """The experimental persistent all-levels kernel (WTB200_MEGA=1: work queue + completion counters +
     TMA reads of data written by other SMs) must agree with the oracle, for every boundary mode."""
     monkeypatch.setenv("WTB200_MEGA", "1")
+    monkeypatch.setenv("WTB200_MEGA_RING", ring)   # > 0: intermediate approximations in `ring` reused scratch slots
+    monkeypatch.setenv("WTB200_MEGA_SEG", "64")
     g = torch.Generator().manual_seed(61)
     for mode in MODES:
         for shape, lev in (((5, 300, 200), 3), ((3, 640, 520), 4), ((9, 64, 96), 2)):
