@@ -17,6 +17,7 @@
 #include "matrix_generic.cuh"
 #include "axis1d_fast.cuh"
 #include "matrix_fused.cuh"
+#include "axis1d_fused.cuh"
 #if !defined(WTB_NO_FUSED) && !__has_include("fused2d.cuh")
 #define WTB_NO_FUSED 1
 #endif
@@ -164,6 +165,40 @@ static int dwt_fwd_generic(int ndim, int mode, int levels, int L, const Taps<T>&
         for (int a = 0; a < ndim; ++a) { cur[a] = lv[l].dims[a]; cs[a] = lv[l].approx_strides[a]; }
     }
     for (int l = first_level; l < levels; ++l) {
+        if (ndim == 1 && cs[0] == 1 && !getenv("WTB200_DISABLE_FUSED")) {
+            // group of consecutive levels -> one fused launch (intermediate approximations stay in shared memory;
+            // their scratch buffers are left untouched, see the scratch semantics in include/wtb200.h)
+            int kmax = 5;
+            if (const char* ev = getenv("WTB200_CONVF_K")) { const int v = atoi(ev); if (v >= 1 && v <= CONVF_MAXK) kmax = v; }
+            int k = levels - l < kmax ? levels - l : kmax;
+            bool ok = k >= 2;
+            int64_t nn[CONVF_MAXK + 1];
+            void* hi_ptr[CONVF_MAXK];
+            int64_t hi_bs[CONVF_MAXK];
+            nn[0] = cur[0];
+            for (int j = 0; j < k && ok; ++j) {
+                const wt_level& dj = lv[l + j];
+                nn[j + 1] = dj.dims[0];
+                hi_ptr[j] = dj.details;
+                hi_bs[j] = dj.details_batch_stride;
+                if (dj.strides[0] != 1 || dj.approx_strides[0] != 1) ok = false;
+            }
+            if (ok) {
+                T flo[16], fhi[16];
+                if (L <= 16) for (int q = 0; q < L; ++q) { flo[q] = taps.lo[L - 1 - q]; fhi[q] = taps.hi[L - 1 - q]; }
+                const wt_level& dl = lv[l + k - 1];
+                cudaError_t e = cudaSuccess;
+                if (L <= 16 && launch_conv1d_fused<T>(L, k, nn, mode, src, cbs, batch, hi_ptr, hi_bs, (T*)dl.approx,
+                                                      dl.approx_batch_stride, flo, fhi, st, &e)) {
+                    g_launches.fetch_add(1, std::memory_order_relaxed);
+                    if (e != cudaSuccess) return cuda_fail(e, "conv1d_fused_kernel");
+                    src = (const T*)dl.approx; cbs = dl.approx_batch_stride;
+                    cur[0] = dl.dims[0]; cs[0] = dl.approx_strides[0];
+                    l += k - 1;
+                    continue;
+                }
+            }
+        }
         const wt_level& d = lv[l];
         T* det = (T*)d.details;
         T* app = (T*)d.approx;

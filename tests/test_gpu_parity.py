@@ -650,3 +650,18 @@ def test_separable_matrix_2d_is_orthogonal_and_inverts():
     assert abs(energy - float(x.pow(2).sum())) <= 1e-9 * energy
     rec = wt.MatrixWaverec2("db4")(c)
     assert float((rec - x).abs().max()) <= 1e-10
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_wavedec_1d_fused_multilevel_kernel_long_signals(dtype):
+    """Long 1-D signals take the fused multi-level kernel (several CTAs per signal, halos between chunks,
+    boundary extension at both ends); periodic mode and short levels fall back to the per-level kernels."""
+    g = torch.Generator().manual_seed(131)
+    for wav, n, level in (("db4", 100_003, 7), ("haar", 65_536, 9), ("sym5", 40_000, 6), ("db8", 70_001, 5), ("db2", 33_333, 11)):
+        x = torch.randn((3, n), generator=g, dtype=torch.float64).to(dtype)
+        for mode in MODES:
+            want = P.wavedec(x, wav, mode=mode, level=level)
+            got = wt.wavedec(x.to(DEV), wav, mode=mode, level=level)
+            _cmp_tree(got, want, f"wavedec fused {wav} n={n} L{level} {mode}")
+            rec = wt.waverec(got, wav)
+            assert_close_rel(rec[..., :n], x, scale=10 * float(x.abs().max()), what=f"round trip {wav} {mode}")

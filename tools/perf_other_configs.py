@@ -58,6 +58,8 @@ if "1d" in which:
     report("wavedec db5 L10 periodic 32x1e6 f32 (speed-test cfg)", (ms, host, gr), nbytes(x) + nbytes(c))
     ms, r, host, gr = timeit(lambda: wt.waverec(c, "db5"))
     report("waverec of it", (ms, host, gr), nbytes(r) + nbytes(c))
+    ms, c, host, gr = timeit(lambda: wt.wavedec(x, "db5", mode="reflect", level=10))
+    report("wavedec db5 L10 reflect 32x1e6 f32 (fused multi-level kernel)", (ms, host, gr), nbytes(x) + nbytes(c))
 if "3d" in which:
     x = torch.randn(8, 256, 256, 256, device="cuda")
     ms, c, host, gr = timeit(lambda: wt.wavedec3(x, "sym4", level=3))
