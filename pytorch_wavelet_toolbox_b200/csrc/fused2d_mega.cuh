@@ -1,4 +1,5 @@
-// fused2d_mega.cuh -- ALL levels of a float32 2-D analysis in ONE persistent kernel.
+// fused2d_mega.cuh -- ALL levels of a float32 2-D analysis in ONE persistent kernel (EXPERIMENTAL, off by
+// default: WTB200_MEGA=1).
 //
 // One launch per level makes every approximation band cA_l a round trip through HBM (+33 % traffic
 // for db4 L4).  This kernel runs the per-level strip algorithm of fwd2d_strip_f32_kernel over a work
@@ -6,10 +7,15 @@
 //
 //     period p :  level-1 items of image p, level-2 items of image p-1, level-3 items of image p-2, ...
 //
-// so that cA_1 of an image is consumed one period (~20 us, ~130 MB of traffic) after it was produced
-// -- while it is still resident in the 126 MB L2 -- and never has to be fetched from HBM.  L2 cache
-// hints steer the replacement: streaming input loads and detail stores are evict_first, approximation
-// stores evict_last.
+// The idea was that cA_1 of an image, consumed one period (~20 us) after it was produced, would still be
+// resident in the 126 MB L2.  MEASURED (profiles/r01_mega_*, tools/ncu_mega_ring.sh): it is not -- DRAM
+// traffic stays at 5.7 GB read + 5.7 GB written per 64-image step whether the L2 cache hints
+// (evict_first for streaming loads / detail stores, evict_last for approximation stores) are on or off
+// and whether or not the approximations are confined to a ring of 2-4 reused scratch slots
+// (WTB200_MEGA_RING) -- and the kernel is 10 % slower than the per-level launches.  It is kept because the
+// scheduling machinery (queue, completion counters, write-after-read protection of the slot ring, TMA
+// reads of data produced by other SMs) is correct, tested in every boundary mode, and the starting point
+// for whatever keeps cA on chip next.
 //
 //   * persistent CTAs (3 per SM) fetch item indices from a global atomic counter; an item of level l+1
 //     waits (ld.acquire spin by one thread) until the per-(level, image) completion counter of level l

@@ -71,7 +71,8 @@ def _no_autograd(*tensors: torch.Tensor, wavelet: Any = None) -> None:
         any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors) or any_requires_grad(wavelet)
     ):
         raise NotImplementedError(
-            "pytorch_wavelet_toolbox_b200 kernels are forward-only in this version; "
+            "gradients are implemented for the data path of wavedec/waverec, wavedec2/waverec2 and "
+            "wavedec3/waverec3 only (not for learnable filter taps, not through the matrix transforms); "
             "call under torch.no_grad() or detach the inputs."
         )
 
