@@ -97,6 +97,9 @@ class _Plan:
     levels: list[_Level] = field(default_factory=list)   # finest first
     approx_off: int = 0
     item_elems: int = 0
+    itemsize: int = 4
+    dims_c: Any = None           # (array, pointer) of in_dims as int64, built once
+    levels_c: Any = None         # (bytes of the wt_level[] template, per-level offsets), built on first use
 
     @property
     def nbands(self) -> int:
@@ -137,13 +140,51 @@ def _make_plan_cached(in_dims: tuple, filt_len: int, levels: int, itemsize: int)
         lv.det_off = off
         off += (plan.nbands - 1) * lv.plane
     plan.item_elems = off
+    plan.itemsize = itemsize
+    plan.dims_c = N.i64_array(plan.in_dims)
     return plan
+
+
+@functools.lru_cache(maxsize=1024)
+def _pads_ok(dims: tuple, filt_len: int, level: int, mode: str, itemsize: int):
+    """None when every level can be padded in this mode, else the exception the reference's F.pad raises."""
+    plan = _make_plan_cached(dims, filt_len, level, itemsize)
+    cur = dims
+    try:
+        for lv in plan.levels:
+            check_pad_feasible(mode, cur, filt_len)
+            cur = lv.dims
+    except RuntimeError as ex:
+        return str(ex)
+    return None
+
+
+def _check_pads(dims: tuple, filt_len: int, level: int, mode: str, plan: "_Plan") -> None:
+    msg = _pads_ok(dims, filt_len, level, mode, plan.itemsize)
+    if msg is not None:
+        raise RuntimeError(msg)
 
 
 def _view_band(buf: torch.Tensor, off: int, lv: _Level) -> torch.Tensor:
     """View of one band [batch, *dims] inside the packed buffer [batch, item_elems]."""
     b = buf.shape[0]
     return buf.as_strided((b,) + lv.dims, (buf.stride(0),) + lv.strides, buf.storage_offset() + off)
+
+
+def _view_details(buf: torch.Tensor, lv: _Level, nbands: int) -> list[torch.Tensor]:
+    """The detail bands k = 1 .. nbands-1 of one level as views [batch, *dims]: one strided view
+    [batch, nbands-1, *dims] split along the band axis (two dispatcher calls instead of nbands-1)."""
+    if nbands == 2:
+        return [_view_band(buf, lv.det_off, lv)]
+    b = buf.shape[0]
+    allb = buf.as_strided((b, nbands - 1) + lv.dims, (buf.stride(0), lv.plane) + lv.strides, buf.storage_offset() + lv.det_off)
+    return list(allb.unbind(1))
+
+
+def _result_views(buf: torch.Tensor, plan: "_Plan"):
+    approx = _view_band(buf, plan.approx_off, plan.levels[-1])
+    details = [_view_details(buf, lv, plan.nbands) for lv in reversed(plan.levels)]
+    return approx, details
 
 
 # --------------------------------------------------------------------------------------
@@ -169,10 +210,7 @@ def _analysis(data: torch.Tensor, wavelet: Any, mode: Optional[str], level: Opti
     if filt_len < 2 or filt_len > N.WT_MAX_FILT_LEN:
         raise ValueError(f"filter length {filt_len} not supported (2..{N.WT_MAX_FILT_LEN})")
     plan = _make_plan(dims, filt_len, level, x.element_size())
-    cur = dims
-    for lv in plan.levels:
-        check_pad_feasible(mode, cur, filt_len)
-        cur = lv.dims
+    _check_pads(dims, filt_len, level, mode, plan)
     if torch.is_grad_enabled() and (x.requires_grad or any_requires_grad(wav)):
         from ._autograd import analysis_with_grad
 
@@ -184,10 +222,7 @@ def _analysis(data: torch.Tensor, wavelet: Any, mode: Optional[str], level: Opti
     batch = x.shape[0]
     if on_host and batch > 1 and x[0].numel() * x.element_size() * batch >= HOST_PIPELINE_MIN_BYTES:
         buf = _analysis_host_pipeline(x, plan, mode, dec_lo, dec_hi, dev)
-        approx = _view_band(buf, plan.approx_off, plan.levels[-1])
-        details = []
-        for lv in reversed(plan.levels):
-            details.append([_view_band(buf, lv.det_off + (k - 1) * lv.plane, lv) for k in range(1, plan.nbands)])
+        approx, details = _result_views(buf, plan)
         return approx, details, f
     with torch.cuda.device(dev):
         xd = x.to(dev, non_blocking=True) if on_host else x
@@ -204,10 +239,7 @@ def _analysis(data: torch.Tensor, wavelet: Any, mode: Optional[str], level: Opti
             host.copy_(buf, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             buf = host
-    approx = _view_band(buf, plan.approx_off, plan.levels[-1])
-    details = []
-    for lv in reversed(plan.levels):
-        details.append([_view_band(buf, lv.det_off + (k - 1) * lv.plane, lv) for k in range(1, plan.nbands)])
+    approx, details = _result_views(buf, plan)
     return approx, details, f
 
 
@@ -269,26 +301,42 @@ def _analysis_host_pipeline(x: torch.Tensor, plan: _Plan, mode: str, dec_lo, dec
 
 
 def _fill_levels(plan: _Plan, buf: torch.Tensor, scratch: torch.Tensor):
+    """``wt_level[levels]`` for this call: the shape part is a per-plan template (copied with one memcpy),
+    only the pointers and batch strides are written per call."""
     nl = len(plan.levels)
-    arr = (N.WtLevel * nl)()
+    tmpl = plan.levels_c
+    if tmpl is None:
+        arr0 = (N.WtLevel * nl)()
+        offs = []
+        soff = 0
+        for i, lv in enumerate(plan.levels):
+            d = arr0[i]
+            d.band_stride = lv.plane
+            for a in range(plan.ndim):
+                d.dims[a] = lv.dims[a]
+                d.strides[a] = lv.strides[a]
+                d.approx_strides[a] = lv.strides[a]
+            if i == nl - 1:
+                offs.append((lv.det_off, plan.approx_off, True))
+            else:
+                offs.append((lv.det_off, soff, False))
+                soff += lv.plane
+        tmpl = plan.levels_c = (bytes(arr0), tuple(offs))
+    raw, offs = tmpl
+    arr = (N.WtLevel * nl).from_buffer_copy(raw)
     es = buf.element_size()
-    soff = 0
-    for i, lv in enumerate(plan.levels):
+    bptr, sptr = buf.data_ptr(), scratch.data_ptr()
+    bstride, sstride = buf.stride(0), scratch.stride(0)
+    for i, (det_off, a_off, in_buf) in enumerate(offs):
         d = arr[i]
-        d.details = buf.data_ptr() + lv.det_off * es
-        d.details_batch_stride = buf.stride(0)
-        d.band_stride = lv.plane
-        for a in range(plan.ndim):
-            d.dims[a] = lv.dims[a]
-            d.strides[a] = lv.strides[a]
-            d.approx_strides[a] = lv.strides[a]
-        if i == nl - 1:
-            d.approx = buf.data_ptr() + plan.approx_off * es
-            d.approx_batch_stride = buf.stride(0)
+        d.details = bptr + det_off * es
+        d.details_batch_stride = bstride
+        if in_buf:
+            d.approx = bptr + a_off * es
+            d.approx_batch_stride = bstride
         else:
-            d.approx = scratch.data_ptr() + soff * es
-            d.approx_batch_stride = scratch.stride(0)
-            soff += lv.plane
+            d.approx = sptr + a_off * es
+            d.approx_batch_stride = sstride
     return arr
 
 
@@ -313,7 +361,7 @@ def _run_fwd(xd: torch.Tensor, plan: _Plan, mode: str, dec_lo, dec_hi, buf: torc
     batch = xd.shape[0]
     lo_arr, lo_p = _taps_c(dec_lo, dt)
     hi_arr, hi_p = _taps_c(dec_hi, dt)
-    dims_arr, dims_p = N.i64_array(plan.in_dims)
+    dims_arr, dims_p = plan.dims_c
     xs_arr, xs_p = N.i64_array(xd.stride()[1:])
     levels = _fill_levels(plan, buf, scratch)
     code = _dtype_code(dt)
