@@ -220,3 +220,31 @@ def test_separable_matrix_nd_argument_errors():
         wt.MatrixWaverec3("haar")((torch.zeros(2, 4, 4, 4), (torch.zeros(2, 4, 4, 4),)))
     with pytest.warns(DeprecationWarning):
         wt.MatrixWavedec2("haar", 2, boundary="qr")
+
+
+def test_separable_matrix_level_walk_matches_the_reference_warning(capsys):
+    """The level walk of MatrixWavedec2/3 (operator sizes, padded axes, early stop with the reference's
+    stderr warning, matmul_transform_2.py:381-405 / matmul_transform_3.py:163-196) is host logic: check it
+    here, and against the unmodified reference when it is importable."""
+    from pytorch_wavelet_toolbox_b200.matrix_fwt_nd import _level_sizes
+
+    sizes, pads = _level_sizes((33, 20), 4, 2, 2)
+    assert sizes == [(34, 20), (18, 10)] and pads == [(True, False), (True, False)]
+    assert capsys.readouterr().err == ""
+    sizes, pads = _level_sizes((12, 9, 16), 4, 3, 3)
+    assert sizes == [(12, 10, 16), (6, 6, 8)] and pads == [(False, True, False), (False, True, False)]
+    ours = capsys.readouterr().err
+    assert "only computed up to the decomposition level 2" in ours and "(3, 3,4)" in ours
+
+    from oracle.ref_import import import_reference, reference_available
+    if not reference_available():
+        return
+    ptwt = import_reference()
+    x = torch.randn(12, 9, 16, dtype=torch.float64)
+    ptwt.MatrixWavedec3("db2", 3)(x)
+    ref = capsys.readouterr().err
+    assert ref == ours
+    _level_sizes((20, 12), 6, 3, 2)
+    ours2 = capsys.readouterr().err
+    ptwt.MatrixWavedec2("db3", 3)(torch.randn(20, 12, dtype=torch.float64))
+    assert capsys.readouterr().err == ours2
