@@ -103,6 +103,21 @@ def test_port_equals_reference_when_present():
     for a, b in zip(r, p):
         assert (a - b).abs().max() < 1e-13
     assert (ptwt.MatrixWaverec("db4")(r) - P.MatrixWaverec("db4")(p)).abs().max() < 1e-12
+    # separable 2-D / 3-D boundary-wavelet transforms: even and odd extents, every mode of the
+    # odd-sample padding
+    for odd_mode in ("zero", "constant", "reflect", "periodic", "symmetric"):
+        x2 = torch.randn(2, 27, 34, generator=g, dtype=torch.float64)
+        r = ptwt.MatrixWavedec2("db3", 2, odd_coeff_padding_mode=odd_mode)(x2)
+        p = P.MatrixWavedec2("db3", 2, odd_coeff_padding_mode=odd_mode)(x2)
+        for a, b in zip(flatten_coeffs(r), flatten_coeffs(p)):
+            assert a.shape == b.shape and (a - b).abs().max() < 1e-12
+        assert (ptwt.MatrixWaverec2("db3")(r) - P.MatrixWaverec2("db3")(p)).abs().max() < 1e-11
+        x3 = torch.randn(2, 9, 12, 11, generator=g, dtype=torch.float64)
+        r = ptwt.MatrixWavedec3("db2", 2, odd_coeff_padding_mode=odd_mode)(x3)
+        p = P.MatrixWavedec3("db2", 2, odd_coeff_padding_mode=odd_mode)(x3)
+        for a, b in zip(flatten_coeffs(r), flatten_coeffs(p)):
+            assert a.shape == b.shape and (a - b).abs().max() < 1e-12
+        assert (ptwt.MatrixWaverec3("db2")(r) - P.MatrixWaverec3("db2")(p)).abs().max() < 1e-11
 
 
 def test_known_answer_ripples_haar():
