@@ -216,6 +216,16 @@ int wt_matrix_axis_inv(int dtype, int filt_len, const double* rec_lo, const doub
 uint64_t wt_launch_count(void);
 void wt_launch_count_reset(void);
 
+/* Tuning / test switches (NOT part of the drop-in surface).  Every switch is also read ONCE from the
+ * environment variable WTB200_<NAME> when the library is first used; no transform call reads the environment.
+ * Names: DISABLE_FUSED (general kernels only), NO_WPAIR (one launch per 2-D analysis level), WPAIR_SEG,
+ * WPAIR_MIN, WPAIR_DEEP, CHUNK, STREAMS, NO_AUX_STREAM, ENABLE_PAIR, MEGA, ... (csrc/knobs.cuh).
+ * wt_set_knob returns 0 or WT_EINVAL for an unknown name; wt_get_knob returns 1 and the value when the switch
+ * is set, 0 when it is not, WT_EINVAL for an unknown name. */
+int wt_set_knob(const char* name, long long value);
+int wt_unset_knob(const char* name);
+int wt_get_knob(const char* name, long long* value);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,8 @@ from __future__ import annotations
 import ctypes as C
 import os
 from pathlib import Path
-from typing import Optional, Sequence
+import contextlib
+from typing import Iterator, Optional, Sequence
 
 import numpy as np
 
@@ -64,6 +65,9 @@ SIGNATURES = {
                                      _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "wt_launch_count": (C.c_uint64, []),
     "wt_launch_count_reset": (None, []),
+    "wt_set_knob": (C.c_int, [C.c_char_p, C.c_longlong]),
+    "wt_unset_knob": (C.c_int, [C.c_char_p]),
+    "wt_get_knob": (C.c_int, [C.c_char_p, C.POINTER(C.c_longlong)]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -128,3 +132,31 @@ def launch_count() -> int:
 
 def launch_count_reset() -> None:
     load().wt_launch_count_reset()
+
+
+def set_knob(name: str, value: Optional[int]) -> None:
+    """Set (or with ``None`` unset) a tuning / test switch of the library (include/wtb200.h, csrc/knobs.cuh)."""
+    lib = load()
+    rc = lib.wt_unset_knob(name.encode()) if value is None else lib.wt_set_knob(name.encode(), int(value))
+    check(rc, f"wt_set_knob({name})")
+
+
+def get_knob(name: str) -> Optional[int]:
+    v = C.c_longlong(0)
+    rc = load().wt_get_knob(name.encode(), C.byref(v))
+    if rc < 0:
+        check(rc, f"wt_get_knob({name})")
+    return int(v.value) if rc == 1 else None
+
+
+@contextlib.contextmanager
+def knobs(**values: Optional[int]) -> Iterator[None]:
+    """``with knobs(NO_WPAIR=1): ...`` -- switches restored on exit."""
+    old = {k: get_knob(k) for k in values}
+    try:
+        for k, v in values.items():
+            set_knob(k, v)
+        yield
+    finally:
+        for k, v in old.items():
+            set_knob(k, v)

@@ -190,7 +190,7 @@ static bool launch_conv1d_fused(int L, int k, const int64_t* n, int mode, const 
     for (int q = 0; q < L; ++q) { p.flo[q] = flo[q]; p.fhi[q] = fhi[q]; }
     const int nk = p.n[k];
     int chunk0 = sizeof(T) == 8 ? 8192 : 16384;                      // level-0 samples per CTA
-    if (const char* ev = getenv("WTB200_CONVF_CHUNK")) { const int v = atoi(ev); if (v >= 64 && v <= 32768) chunk0 = v; }
+    if (knob_is_set(K_CONVF_CHUNK)) { const int v = (int)knob_val(K_CONVF_CHUNK, 0); if (v >= 64 && v <= 32768) chunk0 = v; }
     int tk = chunk0 >> k;
     if (tk < 4) tk = 4;
     tk = (tk + 3) & ~3;

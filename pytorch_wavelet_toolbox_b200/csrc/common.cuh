@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "../../include/wtb200.h"
+#include "knobs.cuh"
 
 namespace wtb {
 

@@ -676,7 +676,7 @@ static cudaError_t launch_fwd2d_level(const T* x, int64_t B, int H, int W, int64
     size_t smem = Gm::smem_bytes(sizeof(T));
     auto kern = tma ? fwd2d_strip_kernel<T, L, TW, true, NSTG> : fwd2d_strip_kernel<T, L, TW, false, NSTG>;
     if constexpr (sizeof(T) == 4 && TW == 64 && NSTG == 2) {
-        if (!getenv("WTB200_NO_FFMA2")) {
+        if (!knob_on(K_NO_FFMA2)) {
             for (int m = 0; m < L / 2; ++m) {
                 p.pl[m] = make_float2(taps.lo[L - 1 - 2 * m], taps.lo[L - 2 - 2 * m]);
                 p.ph[m] = make_float2(taps.hi[L - 1 - 2 * m], taps.hi[L - 2 - 2 * m]);
@@ -730,8 +730,12 @@ bool try_pair<float>(const float* x, int64_t B, int H, int W, int64_t x_bs, int6
     }
 }
 
+template <typename T>
+static bool try_wpair(const T*, int64_t, int, int, int64_t, int64_t, const wt_level&, const wt_level&, int, int,
+                      const Taps<T>&, cudaStream_t, uint64_t*, cudaError_t*);
+
 static bool fused2d_fwd_covers(int ndim, int L) {
-    return ndim == 2 && !(L & 1) && L <= 16 && !getenv("WTB200_DISABLE_FUSED");
+    return ndim == 2 && !(L & 1) && L <= 16 && !knob_on(K_DISABLE_FUSED);
 }
 
 // Try the fused path for the first levels of a 2-D analysis; *first_generic receives the number
@@ -774,11 +778,11 @@ static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* 
     // kernel in fused2d_mega.cuh is the way to use that effect.)
     int64_t chunk = 0;   // images per chunk
     int nstreams = 2;
-    if (const char* ev = getenv("WTB200_CHUNK")) chunk = atoll(ev);
+    if (knob_is_set(K_CHUNK)) chunk = knob_val(K_CHUNK, 0);
     else if (levels >= 2 && batch >= 16 && (int64_t)batch * dims[0] * dims[1] >= (int64_t(1) << 27)) chunk = (batch + 1) / 2;
-    if (const char* ev = getenv("WTB200_STREAMS")) nstreams = atoi(ev) >= 2 ? 2 : 1;
-    if (const char* ev = getenv("WTB200_SPLIT")) {   // legacy knob: number of equal chunks, no scratch reuse change
-        const int ns = atoi(ev);
+    if (knob_is_set(K_STREAMS)) nstreams = knob_val(K_STREAMS, 2) >= 2 ? 2 : 1;
+    if (knob_is_set(K_SPLIT)) {   // legacy knob: number of equal chunks, no scratch reuse change
+        const int ns = (int)knob_val(K_SPLIT, 0);
         chunk = ns > 1 ? (batch + ns - 1) / ns : 0;
     }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -845,11 +849,25 @@ static int fused2d_fwd_run(int ndim, int mode, int levels, int L, const double* 
     int64_t sbs = xbs, srs = xs[0];
     int64_t H = dims[0], W = dims[1];
     uint64_t launches = 0;
-    const char* ev = getenv("WTB200_FWD2D_VARIANT");
-    const int variant = ev ? atoi(ev) : 0;
+    const int variant = (int)knob_val(K_FWD2D_VARIANT, 0);
     for (int l = 0; l < levels; ++l) {
         const wt_level& d = lv[l];
         if (H >= (1 << 30) || W >= (1 << 30)) break;
+        if (l + 1 < levels && (int64_t)batch * H * W >= knob_val(K_WPAIR_MIN, int64_t(1) << 24) && (l == 0 || knob_on(K_WPAIR_DEEP))) {
+            // two levels in one launch of independent warps (fused2d_wpair.cuh): cA_{l+1} stays in shared memory
+            cudaError_t pe = cudaSuccess;
+            if (try_wpair<T>(src, batch, (int)H, (int)W, sbs, srs, lv[l], lv[l + 1], L, mode, taps, st, &launches, &pe)) {
+                g_launches.fetch_add(launches, std::memory_order_relaxed);
+                launches = 0;
+                if (pe != cudaSuccess) return cuda_fail(pe, "fwd2d_wpair_kernel");
+                const wt_level& d2 = lv[l + 1];
+                src = (const T*)d2.approx; sbs = d2.approx_batch_stride; srs = d2.approx_strides[0];
+                H = d2.dims[0]; W = d2.dims[1];
+                ++l;
+                *first_generic = l + 1;
+                continue;
+            }
+        }
         if (l + 1 < levels) {
             // two levels in one launch: the level-(l+1) approximation never leaves the SM
             cudaError_t pe = cudaSuccess;

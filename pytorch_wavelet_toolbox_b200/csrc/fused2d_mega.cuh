@@ -318,8 +318,7 @@ static size_t mega_workspace_bytes(int levels, int64_t batch) {
 }
 
 static bool mega2d_enabled() {
-    const char* e = getenv("WTB200_MEGA");
-    return e && atoi(e) != 0;
+    return knob_on(K_MEGA);
 }
 
 template <int L>
@@ -356,7 +355,7 @@ static int launch_fwd2d_mega(int mode, int levels, const double* dlo, const doub
             if (((uintptr_t)m.out[k] & 15) || (m.out_bs[k] & 3) || (m.out_rs[k] & 3) || m.out_rs[k] < (m.Mw + 3) / 4 * 4) m.vec_store = 0;
         constexpr int HH = Gm::HALO / 2;
         int seg_target = 256;
-        if (const char* ev = getenv("WTB200_MEGA_SEG")) { const int v = atoi(ev); if (v >= 16 && v <= 4096) seg_target = v; }
+        if (knob_is_set(K_MEGA_SEG)) { const int v = (int)knob_val(K_MEGA_SEG, 0); if (v >= 16 && v <= 4096) seg_target = v; }
         int nseg = (m.Mh + seg_target - 1) / seg_target;
         int seg = ((m.Mh + nseg - 1) / nseg + HH + 15) / 16 * 16 - HH;
         if (seg < 16 - HH) seg = 16 - HH;
@@ -369,7 +368,7 @@ static int launch_fwd2d_mega(int mode, int levels, const double* dlo, const doub
     }
     p.items_per_period = ipp;
     p.ring = 0;
-    if (const char* ev = getenv("WTB200_MEGA_RING")) { const int v = atoi(ev); if (v >= 2 && v <= batch) p.ring = v; }
+    if (knob_is_set(K_MEGA_RING)) { const int v = (int)knob_val(K_MEGA_RING, 0); if (v >= 2 && v <= batch) p.ring = v; }
     if ((int64_t)ipp * (batch + levels) >= (int64_t(1) << 31)) return 0;
     float tl[16], th[16];
     for (int k = 0; k < L; ++k) { tl[k] = (float)dlo[k]; th[k] = (float)dhi[k]; }
@@ -383,7 +382,7 @@ static int launch_fwd2d_mega(int mode, int levels, const double* dlo, const doub
     }
     cudaError_t e = cudaMemsetAsync(ws, 0, mega_workspace_bytes(levels, batch), st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
-    const bool hints = !getenv("WTB200_MEGA_NOHINTS");
+    const bool hints = !knob_on(K_MEGA_NOHINTS);
     auto kern = hints ? fwd2d_mega_kernel<L, true> : fwd2d_mega_kernel<L, false>;
     const size_t smem = Fwd2dGeomF<L, 64>::SMEM;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -400,7 +400,7 @@ fwd2d_pair_kernel(const __grid_constant__ Pair2dParams p, const __grid_constant_
 static bool pair2d_supported(int L, int mode) {
     // experimental: correct (tests run it with WTB200_ENABLE_PAIR=1) but at 2 CTAs/SM it is not yet
     // faster than two one-level launches, so it is off by default
-    return !(L & 1) && L >= 2 && L <= 8 && mode != WT_MODE_PERIODIC && getenv("WTB200_ENABLE_PAIR");
+    return !(L & 1) && L >= 2 && L <= 8 && mode != WT_MODE_PERIODIC && knob_on(K_ENABLE_PAIR);
 }
 
 template <int L, int TW2_>
@@ -464,8 +464,7 @@ template <int L>
 static cudaError_t launch_fwd2d_pair(const float* x, int64_t B, int H, int W, int64_t x_bs, int64_t x_rs,
                                      const wt_level& l1, const wt_level& l2, int mode, const Taps<float>& taps,
                                      cudaStream_t st, uint64_t* launches) {
-    const char* ev = getenv("WTB200_PAIR_TW2");
-    if (ev && atoi(ev) == 16)
+    if (knob_val(K_PAIR_TW2, 32) == 16)
         return launch_fwd2d_pair_t<L, 16>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches);
     return launch_fwd2d_pair_t<L, 32>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches);
 }

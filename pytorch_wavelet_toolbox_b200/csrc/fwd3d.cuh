@@ -288,7 +288,7 @@ static bool make_tmap_4d(CUtensorMap* map, const float* base, int64_t B, int64_t
 }
 
 static bool fused3d_fwd_covers(int ndim, int dtype_size, int L) {
-    return ndim == 3 && dtype_size == 4 && !(L & 1) && L >= 2 && L <= 8 && !getenv("WTB200_DISABLE_FUSED");
+    return ndim == 3 && dtype_size == 4 && !(L & 1) && L >= 2 && L <= 8 && !knob_on(K_DISABLE_FUSED);
 }
 
 template <int L, int TH, int TW>
@@ -357,8 +357,8 @@ static cudaError_t launch_fwd3d_level(const float* x, int64_t B, int D, int H, i
     }
     for (int c = 1; c < 3; ++c)
         if (4 * cost[c] <= 3 * cost[0] && cost[c] < cost[best]) best = c;
-    if (const char* ev = getenv("WTB200_FWD3D_TILE")) {
-        const int forced = atoi(ev);
+    if (knob_is_set(K_FWD3D_TILE)) {
+        const int forced = (int)knob_val(K_FWD3D_TILE, -1);
         if (forced >= 0 && forced < 3) best = forced;
     }
     ++*launches;

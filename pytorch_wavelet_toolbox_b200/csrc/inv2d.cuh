@@ -275,7 +275,7 @@ static cudaError_t launch_inv2d_level(const float* const in[4], const int64_t in
 }
 
 static bool fused2d_inv_covers(int ndim, int dtype_size, int L) {
-    return ndim == 2 && dtype_size == 4 && !(L & 1) && L >= 2 && L <= 16 && !getenv("WTB200_DISABLE_FUSED");
+    return ndim == 2 && dtype_size == 4 && !(L & 1) && L >= 2 && L <= 16 && !knob_on(K_DISABLE_FUSED);
 }
 
 // All levels of a float32 2-D synthesis; returns 0 and sets *done = 1 when it handled the request.

@@ -237,7 +237,7 @@ inv3d_tile_kernel(const __grid_constant__ Inv3dParams p, const __grid_constant__
 // host side
 // ------------------------------------------------------------------------------------------
 static bool fused3d_inv_covers(int ndim, int dtype_size, int L) {
-    return ndim == 3 && dtype_size == 4 && !(L & 1) && L >= 2 && L <= 8 && !getenv("WTB200_DISABLE_FUSED");
+    return ndim == 3 && dtype_size == 4 && !(L & 1) && L >= 2 && L <= 8 && !knob_on(K_DISABLE_FUSED);
 }
 
 template <int L>

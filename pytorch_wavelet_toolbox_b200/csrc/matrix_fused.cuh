@@ -238,7 +238,7 @@ static bool launch_mat_fwd_fused(int L, int k, const int64_t* n, const int32_t* 
     for (int q = 0; q < L; ++q) { p.flo[q] = taps.lo[L - 1 - q]; p.fhi[q] = taps.hi[L - 1 - q]; }
     const int nk = p.n[k];
     int chunk0 = sizeof(T) == 8 ? 8192 : 16384;                   // level-0 samples per CTA (tools/ab_matrix.py)
-    if (const char* ev = getenv("WTB200_MATF_CHUNK")) { const int v = atoi(ev); if (v >= 64 && v <= 16384) chunk0 = v; }
+    if (knob_is_set(K_MATF_CHUNK)) { const int v = (int)knob_val(K_MATF_CHUNK, 0); if (v >= 64 && v <= 16384) chunk0 = v; }
     int tk = chunk0 >> k;
     if (tk < 4) tk = 4;
     tk = (tk + 3) & ~3;
@@ -458,7 +458,7 @@ static bool launch_mat_inv_fused(int L, int k, const int64_t* n, int64_t keep0, 
     }
     for (int q = 0; q < L; ++q) { p.rlo[q] = (T)rlo[q]; p.rhi[q] = (T)rhi[q]; }
     int chunk = sizeof(T) == 8 ? 2048 : 4096;
-    if (const char* ev = getenv("WTB200_MATI_CHUNK")) { const int v = atoi(ev); if (v >= 64 && v <= 16384) chunk = v; }
+    if (knob_is_set(K_MATI_CHUNK)) { const int v = (int)knob_val(K_MATI_CHUNK, 0); if (v >= 64 && v <= 16384) chunk = v; }
     const int gran = 4 << k;
     chunk = (chunk + gran - 1) / gran * gran;
     if (chunk > p.n[0]) chunk = (p.n[0] + gran - 1) / gran * gran;

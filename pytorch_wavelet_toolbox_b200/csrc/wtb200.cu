@@ -44,6 +44,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 #ifndef WTB_NO_FUSED
 #include "fused2d.cuh"
 #include "fused2d_pair.cuh"
+#include "fused2d_wpair.cuh"
 #include "fused2d_mega.cuh"
 #include "inv2d.cuh"
 #include "fwd3d.cuh"
@@ -165,11 +166,11 @@ static int dwt_fwd_generic(int ndim, int mode, int levels, int L, const Taps<T>&
         for (int a = 0; a < ndim; ++a) { cur[a] = lv[l].dims[a]; cs[a] = lv[l].approx_strides[a]; }
     }
     for (int l = first_level; l < levels; ++l) {
-        if (ndim == 1 && cs[0] == 1 && !getenv("WTB200_DISABLE_FUSED")) {
+        if (ndim == 1 && cs[0] == 1 && !knob_on(K_DISABLE_FUSED)) {
             // group of consecutive levels -> one fused launch (intermediate approximations stay in shared memory;
             // their scratch buffers are left untouched, see the scratch semantics in include/wtb200.h)
             int kmax = 5;
-            if (const char* ev = getenv("WTB200_CONVF_K")) { const int v = atoi(ev); if (v >= 1 && v <= CONVF_MAXK) kmax = v; }
+            if (knob_is_set(K_CONVF_K)) { const int v = (int)knob_val(K_CONVF_K, 0); if (v >= 1 && v <= CONVF_MAXK) kmax = v; }
             int k = levels - l < kmax ? levels - l : kmax;
             bool ok = k >= 2;
             int64_t nn[CONVF_MAXK + 1];
@@ -214,7 +215,7 @@ static int dwt_fwd_generic(int ndim, int mode, int levels, int L, const Taps<T>&
             View<T> lo = band(0), hi = band(1);
             lo.s_n = st_of(0)[0]; hi.s_n = st_of(1)[0];
             bool done1 = false;
-            if (cs[0] == 1 && lo.s_n == 1 && hi.s_n == 1 && cur[0] < (1 << 30) && L <= 16 && !getenv("WTB200_DISABLE_FUSED")) {
+            if (cs[0] == 1 && lo.s_n == 1 && hi.s_n == 1 && cur[0] < (1 << 30) && L <= 16 && !knob_on(K_DISABLE_FUSED)) {
                 Fast1dParams<T> fp;
                 memset(&fp, 0, sizeof(fp));
                 fp.x = src; fp.lo = lo.ptr; fp.hi = hi.ptr;
@@ -329,7 +330,7 @@ static int dwt_inv_generic(int ndim, int levels, int L, const Taps<T>& taps, T* 
             lo.s_n = st_of(0)[0]; hi.s_n = st_of(1)[0];
             View<T> yv{dst, dbs, 0, ds[0]};
             bool done1 = false;
-            if (lo.s_n == 1 && hi.s_n == 1 && ds[0] == 1 && d.dims[0] < (1 << 29) && L <= 16 && !getenv("WTB200_DISABLE_FUSED")) {
+            if (lo.s_n == 1 && hi.s_n == 1 && ds[0] == 1 && d.dims[0] < (1 << 29) && L <= 16 && !knob_on(K_DISABLE_FUSED)) {
                 Fast1dInvParams<T> fp;
                 memset(&fp, 0, sizeof(fp));
                 fp.lo = lo.ptr; fp.hi = hi.ptr; fp.y = dst;
@@ -537,11 +538,11 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
     }
     for (int l = 0; l < levels; ++l) {
         if (n[l] < 2 || (n[l] & 1)) return fail(WT_ESHAPE, "level %d: operator size %lld must be even", l + 1, (long long)n[l]);
-        if (allow_fused && !getenv("WTB200_DISABLE_FUSED")) {
+        if (allow_fused && !knob_on(K_DISABLE_FUSED)) {
             // group of consecutive unpadded levels -> one fused launch
             int k = 0;
             int kmax = 4;  // measured on config 4 (tools/ab_matrix.py): 4 levels x 4096-sample chunks beat 6 x 4096
-            if (const char* ev = getenv("WTB200_MATF_K")) { const int v = atoi(ev); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
+            if (knob_is_set(K_MATF_K)) { const int v = (int)knob_val(K_MATF_K, 0); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
             while (l + k < levels && k < kmax && !padded[l + k] && !(n[l + k] & 1) &&
                    (k == 0 || n[l + k] == n[l + k - 1] / 2))
                 ++k;
@@ -581,7 +582,7 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
         if (total > 0) {
             bool done1 = false;
             cudaError_t e = cudaSuccess;
-            if (n[l] < (1 << 30) && !(L & 1) && L <= 16 && !getenv("WTB200_DISABLE_FUSED")) {
+            if (n[l] < (1 << 30) && !(L & 1) && L <= 16 && !knob_on(K_DISABLE_FUSED)) {
                 Fast1dParams<T> fp;
                 memset(&fp, 0, sizeof(fp));
                 fp.x = p.x; fp.lo = p.lo; fp.hi = p.hi;
@@ -637,12 +638,12 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
         bptr[4 * l + 3] = q;
     }
     for (int l = levels - 1; l >= 0; --l) {
-        if (allow_fused && !getenv("WTB200_DISABLE_FUSED")) {
+        if (allow_fused && !knob_on(K_DISABLE_FUSED)) {
             // group of levels l, l-1, ..., l-k+1 whose intermediate results are not trimmed -> one launch
             // default 1 = per-level kernels: on config 4 the fused synthesis kernel (0.79 ms) is slower than
             // twelve register-blocked per-level launches (0.57 ms); WTB200_MATI_K >= 2 opts in
             int kmax = 1;
-            if (const char* ev = getenv("WTB200_MATI_K")) { const int v = atoi(ev); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
+            if (knob_is_set(K_MATI_K)) { const int v = (int)knob_val(K_MATI_K, 0); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
             int k = 1;
             while (k < kmax && l - k >= 0 && next_len[l - k + 1] == n[l - k + 1] && n[l - k] == 2 * n[l - k + 1]) ++k;
             if (k >= 2) {
@@ -688,7 +689,7 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
         const int64_t total = batch * p.keep;
         if (total > 0) {
             cudaError_t e = cudaSuccess;
-            const bool fast = !getenv("WTB200_DISABLE_FUSED") && launch_mat_inv_fast<T>(p, st, &e);
+            const bool fast = !knob_on(K_DISABLE_FUSED) && launch_mat_inv_fast<T>(p, st, &e);
             if (!fast) {
                 mat_inv_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(p);
                 e = cudaGetLastError();
@@ -726,7 +727,7 @@ static int matrix_axis_t(bool inverse, int L, const double* flo, const double* f
     const int64_t total = outer * (inverse ? keep : n / 2) * inner;
     if (total <= 0) return 0;
     // contiguous axis: the register-blocked 1-D kernels of MatrixWavedec / MatrixWaverec apply directly
-    if (inner == 1 && xas == 1 && yas == 1 && n < (int64_t(1) << 30) && !(L & 1) && L <= 16 && !getenv("WTB200_DISABLE_FUSED")) {
+    if (inner == 1 && xas == 1 && yas == 1 && n < (int64_t(1) << 30) && !(L & 1) && L <= 16 && !knob_on(K_DISABLE_FUSED)) {
         cudaError_t e = cudaSuccess;
         bool done = true;
         // the row index rides on gridDim.y: at most 65535 rows per launch
@@ -761,7 +762,7 @@ static int matrix_axis_t(bool inverse, int L, const double* flo, const double* f
             return 0;
         }
     }
-    if (inner > 1 && !getenv("WTB200_DISABLE_FUSED")) {
+    if (inner > 1 && !knob_on(K_DISABLE_FUSED)) {
         cudaError_t e = cudaSuccess;
         if (launch_mat_axis_blk<T>(p, inverse, st, &e)) {
             g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -943,5 +944,20 @@ int wt_matrix_axis_inv(int dtype, int filt_len, const double* rec_lo, const doub
 
 uint64_t wt_launch_count(void) { return g_launches.load(); }
 void wt_launch_count_reset(void) { g_launches.store(0); }
+
+int wt_set_knob(const char* name, long long value) {
+    const int k = knob_find(name);
+    if (k < 0) return fail(WT_EINVAL, "unknown knob '%s'", name ? name : "(null)");
+    knob_table().v[k].store(value, std::memory_order_relaxed);
+    return 0;
+}
+int wt_unset_knob(const char* name) { return wt_set_knob(name, KNOB_UNSET); }
+int wt_get_knob(const char* name, long long* value) {
+    const int k = knob_find(name);
+    if (k < 0) return fail(WT_EINVAL, "unknown knob '%s'", name ? name : "(null)");
+    const long long v = knob_table().v[k].load(std::memory_order_relaxed);
+    if (value) *value = v == KNOB_UNSET ? 0 : v;
+    return v == KNOB_UNSET ? 0 : 1;
+}
 
 }  // extern "C"

@@ -37,6 +37,23 @@ def golden():
     return manifest, arrays
 
 
+@pytest.fixture
+def knob():
+    """Set tuning / test switches of libwtb200 for one test: ``knob("NO_WPAIR", 1)`` (restored afterwards)."""
+    from pytorch_wavelet_toolbox_b200 import _native
+
+    saved = {}
+
+    def _set(name, value):
+        if name not in saved:
+            saved[name] = _native.get_knob(name)
+        _native.set_knob(name, value)
+
+    yield _set
+    for name, value in saved.items():
+        _native.set_knob(name, value)
+
+
 def flatten_coeffs(coeffs):
     """Coefficient pytree -> flat tensor list in the order the golden fixtures use."""
     out = []

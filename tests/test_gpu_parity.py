@@ -423,22 +423,18 @@ def test_host_pipeline_equals_device_path(monkeypatch):
         assert torch.equal(a, b.cpu())
 
 
-def test_pair_kernel_when_enabled(monkeypatch):
+def test_pair_kernel_when_enabled(knob):
     """The experimental two-level fused kernel (WTB200_ENABLE_PAIR=1) must agree with the oracle."""
-    import os
-
-    monkeypatch.setenv("WTB200_ENABLE_PAIR", "1")
+    knob("ENABLE_PAIR", 1)
+    knob("NO_WPAIR", 1)
     g = torch.Generator().manual_seed(22)
-    try:
-        for mode in ("zero", "constant", "reflect", "symmetric"):
-            for shape in ((300, 200), (129, 517), (64, 64)):
-                x = torch.randn((2,) + shape, generator=g)
-                _cmp_tree(wt.wavedec2(x.to(DEV), "db4", mode=mode, level=4 if min(shape) > 100 else 2),
-                          P.wavedec2(x, "db4", mode=mode, level=4 if min(shape) > 100 else 2), f"pair {mode} {shape}")
-                _cmp_tree(wt.wavedec2(x.to(DEV), "db2", mode=mode, level=3), P.wavedec2(x, "db2", mode=mode, level=3),
-                          f"pair db2 {mode} {shape}")
-    finally:
-        os.environ.pop("WTB200_ENABLE_PAIR", None)
+    for mode in ("zero", "constant", "reflect", "symmetric"):
+        for shape in ((300, 200), (129, 517), (64, 64)):
+            x = torch.randn((2,) + shape, generator=g)
+            _cmp_tree(wt.wavedec2(x.to(DEV), "db4", mode=mode, level=4 if min(shape) > 100 else 2),
+                      P.wavedec2(x, "db4", mode=mode, level=4 if min(shape) > 100 else 2), f"pair {mode} {shape}")
+            _cmp_tree(wt.wavedec2(x.to(DEV), "db2", mode=mode, level=3), P.wavedec2(x, "db2", mode=mode, level=3),
+                      f"pair db2 {mode} {shape}")
 
 
 def test_separable_front_ends():
@@ -520,12 +516,12 @@ def test_tiny_and_ragged_shapes():
 
 
 @pytest.mark.parametrize("ring", ["0", "2", "3"])
-def test_persistent_multilevel_kernel_when_enabled(monkeypatch, ring):
+def test_persistent_multilevel_kernel_when_enabled(knob, ring):
     """The experimental persistent all-levels kernel (WTB200_MEGA=1: work queue + completion counters +
     TMA reads of data written by other SMs) must agree with the oracle, for every boundary mode."""
-    monkeypatch.setenv("WTB200_MEGA", "1")
-    monkeypatch.setenv("WTB200_MEGA_RING", ring)   # > 0: intermediate approximations in `ring` reused scratch slots
-    monkeypatch.setenv("WTB200_MEGA_SEG", "64")
+    knob("MEGA", 1)
+    knob("MEGA_RING", int(ring))   # > 0: intermediate approximations in `ring` reused scratch slots
+    knob("MEGA_SEG", 64)
     g = torch.Generator().manual_seed(61)
     for mode in MODES:
         for shape, lev in (((5, 300, 200), 3), ((3, 640, 520), 4), ((9, 64, 96), 2)):
@@ -582,10 +578,10 @@ def test_calls_can_be_captured_in_a_cuda_graph():
     assert not torch.equal(leaves(eager)[0], want[0])
 
 
-def test_fused_matrix_synthesis_kernel_when_enabled(monkeypatch):
+def test_fused_matrix_synthesis_kernel_when_enabled(knob):
     """WTB200_MATI_K >= 2 runs groups of synthesis levels as one kernel (intermediate approximations stay in
     shared memory); it must agree with the oracle like the default per-level kernels."""
-    monkeypatch.setenv("WTB200_MATI_K", "4")
+    knob("MATI_K", 4)
     g = torch.Generator().manual_seed(83)
     for wav, n, level in (("db2", 64, 3), ("db4", 256, 4), ("db6", 4096, 6), ("sym5", 1000, 5), ("haar", 48, 3),
                           ("db3", 202, 4)):
@@ -597,10 +593,10 @@ def test_fused_matrix_synthesis_kernel_when_enabled(monkeypatch):
 
 
 @pytest.mark.parametrize("tile", ["0", "1", "2"])
-def test_wavedec3_every_tile_shape(monkeypatch, tile):
+def test_wavedec3_every_tile_shape(knob, tile):
     """The 3-D analysis kernel is instantiated for three tile shapes (16x32, 11x44, 8x64); the host picks by
     waste, WTB200_FWD3D_TILE forces one.  All must agree with the oracle on ragged extents and every mode."""
-    monkeypatch.setenv("WTB200_FWD3D_TILE", tile)
+    knob("FWD3D_TILE", int(tile))
     g = torch.Generator().manual_seed(97 + int(tile))
     for mode in MODES:
         for shape, wav, lev in (((2, 37, 50, 91), "sym4", 2), ((1, 20, 131, 45), "db2", 2), ((3, 16, 18, 140), "haar", 1)):
