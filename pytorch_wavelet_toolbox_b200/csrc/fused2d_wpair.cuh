@@ -16,9 +16,10 @@
 //     output rows it contributes to, held as FFMA2 accumulators in registers
 //     (acc[i] += dec[2(i-k)+1] * row[2k] + dec[2(i-k)] * row[2k+1]); one output row completes per
 //     pair and goes straight to HBM (three detail bands, 128-bit stores, 512 contiguous bytes/warp);
-//   * the completed approximation row goes to an 8-row ring in shared memory (the only exchange
-//     between lanes); level 2 reads it back with lane <-> 2 level-2 columns, same row pass, same
-//     scatter accumulators, and stores its four bands;
+//   * the completed approximation row goes to a two-row buffer in shared memory (the only exchange
+//     between lanes); level 2 reads it back with lane <-> 2 level-2 columns, runs the same row pass
+//     and keeps the row-filtered lines in an 8-row ring; its column pass gathers the L ring rows of
+//     one output row (no level-2 state in registers, one copy of the code) and stores the four bands;
 //   * boundary extension: out-of-range input samples are patched into the staged tile from the
 //     extension source (all modes but periodic; zero fill is TMA's out-of-bounds fill); the level-2
 //     extension of the approximation band is served from the ring (rows) and by patching the ring
@@ -52,7 +53,7 @@ struct WPairParams {
     float2 vl[8], vh[8];       // column pass: {dec[m], dec[m]}
 };
 
-template <int L>
+template <int L, int NSTG_ = 3>
 struct WPairGeom {
     static constexpr int HALO = L - 2, NA = L / 2;
     static constexpr int HAL = (HALO + 3) / 4 * 4;          // left halo of the staged tile, 16-byte aligned
@@ -64,15 +65,17 @@ struct WPairGeom {
     static constexpr int NV1 = OFF1 + L + 6, NV1_4 = (NV1 + 3) / 4;
     static constexpr int TILE_W = 8 * 31 + 4 * NV1_4;       // staged input columns
     static constexpr int NV2 = OFF2 + L + 2, NV2_4 = (NV2 + 3) / 4;
-    static constexpr int RP = 4 * 31 + 4 * NV2_4;           // pitch of the approximation ring
-    static constexpr int RING = 8;                          // >= L rows (boundary sources stay resident)
-    static constexpr int ROWS = 4, NSTG = 3;
+    static constexpr int RP1 = TW1;                         // pitch of the two approximation row buffers (the windows of
+                                                            // lanes >= TW2/2 run into the ring behind them: don't-care)
+    static constexpr int R2P = 128;                         // ring row: 64 low-pass | 64 high-pass row-filtered samples
+    static constexpr int RING = 8;                          // >= L rows (the window of one output; boundary sources)
+    static constexpr int ROWS = 4, NSTG = NSTG_;
     static constexpr int STAGE_BYTES = ROWS * TILE_W * 4;
     static constexpr int STAGE_STRIDE = (STAGE_BYTES + 127) / 128 * 128;
-    static constexpr int SMEM = NSTG * STAGE_STRIDE + (RING + 1) * RP * 4 + 64;
+    static constexpr int SMEM = NSTG * STAGE_STRIDE + 2 * RP1 * 4 + RING * R2P * 4 + 8 * NSTG;
     static_assert(L % 2 == 0 && L >= 2 && L <= 8, "wpair kernel: even filter length <= 8");
     static_assert(TILE_W % 4 == 0 && TILE_W / 2 <= 256, "tile row must fit one TMA box of 8-byte elements");
-    static_assert(RING >= L, "ring too small for the boundary sources");
+    static_assert(RING >= L, "ring too small for the window of one output row");
 };
 
 // lo[c], hi[c] for NC consecutive outputs from the register window w (see row_filter8)
@@ -140,65 +143,20 @@ __device__ __forceinline__ void wp_l1_compute(const float* __restrict__ tr, floa
     wp_scatter<L, 2>(acc, lo, hi, p, s);
 }
 
-// Row pass + scatter of one level-2 step: approximation rows rA (even), rB (odd) of the ring (lane window)
-template <int L>
-__device__ __forceinline__ void wp_l2_compute(const float* __restrict__ rA, const float* __restrict__ rB,
-                                              float2 (&acc)[L / 2][4][1], const WPairParams& p, const int s) {
-    using Gm = WPairGeom<L>;
-    float2 lo[2][1], hi[2][1];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const float* src = r ? rB : rA;
-        float w[4 * Gm::NV2_4];
-#pragma unroll
-        for (int q = 0; q < Gm::NV2_4; ++q) {
-            const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
-            w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
-        }
-        float l2[2], h2[2];
-        wp_rowfilt<L, 2, Gm::OFF2>(w, p.pl, p.ph, l2, h2);
-        lo[r][0] = make_float2(l2[0], l2[1]);
-        hi[r][0] = make_float2(h2[0], h2[1]);
-    }
-    wp_scatter<L, 1>(acc, lo, hi, p, s);
-}
-
-// logical slot s becomes physical slot 0 (the fast loop uses compile-time slots starting from 0)
-template <int NA, int NCP>
-__device__ __forceinline__ void wp_rotate(float2 (&acc)[NA][4][NCP], const int s) {
-    if (NA == 1 || s == 0) return;
-    float2 t[NA][4][NCP];
-#pragma unroll
-    for (int i = 0; i < NA; ++i)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-#pragma unroll
-            for (int c = 0; c < NCP; ++c) t[i][k][c] = acc[i][k][c];
-#pragma unroll
-    for (int r = 1; r < NA; ++r)
-        if (s == r) {
-#pragma unroll
-            for (int i = 0; i < NA; ++i)
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-#pragma unroll
-                    for (int c = 0; c < NCP; ++c) acc[i][k][c] = t[(i + r) % NA][k][c];
-        }
-}
-
-template <int L>
-__global__ void __launch_bounds__(32, 12)
+template <int L, int NSTG, int MINB>
+__global__ void __launch_bounds__(32, MINB)
 fwd2d_wpair_kernel(const __grid_constant__ WPairParams p, const __grid_constant__ CUtensorMap tmap) {
-    using Gm = WPairGeom<L>;
+    using Gm = WPairGeom<L, NSTG>;
     constexpr int HALO = Gm::HALO, NA = Gm::NA, HAL = Gm::HAL, HL1 = Gm::HL1, TW1 = Gm::TW1, TW2 = Gm::TW2;
-    constexpr int TILE_W = Gm::TILE_W, RP = Gm::RP, RING = Gm::RING, ROWS = Gm::ROWS, NSTG = Gm::NSTG;
+    constexpr int TILE_W = Gm::TILE_W, RP1 = Gm::RP1, R2P = Gm::R2P, RING = Gm::RING, ROWS = Gm::ROWS;
     constexpr int STG_F = Gm::STAGE_STRIDE / 4;
-    constexpr int FB = NA;                             // groups per fast block: 2 NA level-1 steps, NA level-2 steps
+    constexpr int UNR = (NA & 1) ? NA : (NA / 2 > 0 ? NA / 2 : 1);   // groups per unrolled block: whole slot rotations
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_tile = reinterpret_cast<float*>(smem_raw);                              // [NSTG][ROWS][TILE_W]
-    float* s_ring = reinterpret_cast<float*>(smem_raw + NSTG * Gm::STAGE_STRIDE);    // [RING + 1][RP], last row = 0
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + (RING + 1) * RP);
+    float* s_row = reinterpret_cast<float*>(smem_raw + NSTG * Gm::STAGE_STRIDE);     // [2][RP1] approximation rows
+    float* s_ring = s_row + 2 * RP1;                                                 // [RING][R2P] row-filtered lines
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_ring + RING * R2P);
 
     const int lane = threadIdx.x;
     const int b = p.batch0 + blockIdx.y;
@@ -218,14 +176,21 @@ fwd2d_wpair_kernel(const __grid_constant__ WPairParams p, const __grid_constant_
 
     // ---- segment (long segments come first in the grid, the short ones fill the tail) ---------------
     const int Y0 = p.seg_start[blockIdx.z], Y1 = p.seg_start[blockIdx.z + 1];
-    // approximation rows [a_start, a_end) are computed here; the bottom extension sources (the last RING rows)
-    // are included even when the segment is short
-    const int a_start = max(0, min(2 * (Y0 - NA + 1), p.Mh1 - RING));
+    // Approximation rows [a_start, a_end) are computed here (a_start = -1 is a dummy row that is never written).
+    // The first row is chosen such that every TMA group completes an (even, odd) pair of rows -- the window of a
+    // level-2 output row ends on an odd row, so level 2 runs once per group -- and such that the bottom extension
+    // sources (the last RING rows) are included even when the segment is short.
+    int a_start = 2 * Y0 - HALO - ((NA - 1) & 1);
+    {
+        int amax = p.Mh1 - RING;
+        if ((amax - (NA - 1)) & 1) --amax;
+        a_start = max(min(a_start, amax), -((NA - 1) & 1));
+    }
     const int a_end = min(p.Mh1, 2 * Y1);
+    const int a_lo = max(a_start, 0);                 // first row really written
     const int n1 = a_end - a_start + NA - 1;          // level-1 steps (pairs of input rows)
     const int ngroups = (n1 + 1) / 2;                 // TMA groups of 4 input rows
     const int r_in0 = 2 * a_start - HALO;             // first staged input row
-    const int n2 = Y1 - Y0 + NA - 1;                  // level-2 steps (pairs of approximation rows)
 
     if (lane == 0) {
         tma_prefetch_desc(&tmap);
@@ -233,7 +198,6 @@ fwd2d_wpair_kernel(const __grid_constant__ WPairParams p, const __grid_constant_
         for (int s = 0; s < NSTG; ++s) mbar_init(&bars[s], 1);
         fence_mbar_init();
     }
-    for (int i = lane; i < RP; i += 32) s_ring[RING * RP + i] = 0.f;
     __syncwarp();
     if (lane == 0) {
         for (int s = 0; s < NSTG && s < ngroups; ++s) {
@@ -250,14 +214,14 @@ fwd2d_wpair_kernel(const __grid_constant__ WPairParams p, const __grid_constant_
     // level-1 stores: this lane's 4 columns, running pointer = row `produced` of band 1
     const int col1 = cA0 + 4 * lane;
     const bool store1 = col1 >= own1_lo && col1 < own1_hi;
-    float* pd1 = p.d1 + (int64_t)b * p.d1_bs + (int64_t)a_start * p.d1_rs + col1;
+    float* const pd1 = p.d1 + (int64_t)b * p.d1_bs + (int64_t)a_start * p.d1_rs + col1;
     // level-2 stores: this lane's 2 columns, running pointers = row K2 of the four bands
     const int col2 = X0 + 2 * lane;
     const bool store2 = col2 >= own2_lo && col2 < own2_hi;
     float* po2[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) po2[k] = p.o2[k] + (int64_t)b * p.o2_bs[k] + (int64_t)Y0 * p.o2_rs[k] + col2;
-    // ring patch table of the edge strips: source index (within the ring row) of each out-of-range column
+    // patch table of the edge strips: source index (within the approximation row) of each out-of-range column
     int psrc[4] = {-2, -2, -2, -2};
     if (edge_a) {
 #pragma unroll
@@ -271,120 +235,28 @@ fwd2d_wpair_kernel(const __grid_constant__ WPairParams p, const __grid_constant_
     }
 
     float2 acc1[NA][4][2];
-    float2 acc2[NA][4][1];
 #pragma unroll
     for (int s = 0; s < NA; ++s)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            acc1[s][k][0] = make_float2(0.f, 0.f); acc1[s][k][1] = make_float2(0.f, 0.f);
-            acc2[s][k][0] = make_float2(0.f, 0.f);
-        }
+        for (int k = 0; k < 4; ++k) { acc1[s][k][0] = make_float2(0.f, 0.f); acc1[s][k][1] = make_float2(0.f, 0.f); }
 
-    int s1 = 0, s2 = 0, j2 = 0, produced = a_start;
+    int K2 = Y0;                       // next level-2 output row
+    int produced = a_lo;               // approximation rows [.., produced) are in the ring
     int stage = 0;
     uint32_t par = 0;
-    float* const ring_lane = s_ring + 4 * lane;
-    const float* const tile_lane = s_tile + 8 * lane;
+    float* const row_lane = s_row + 4 * lane;
+    float* const ring_lane = s_ring + 2 * lane;
 
-    // columns of the staged tile outside the image: the L samples next to each border are all any valid output reads
-    auto patch_cols = [&](float* tile, const int rbase) {
-        const int nl = c_in0 < 0 ? -c_in0 : 0;
-        const int l0 = max(nl - L, 0);
-        const int r0 = min(max(p.W - c_in0, 0), TILE_W), r1 = min(r0 + L, TILE_W);
-        const int wl = nl - l0, wb = wl + (r1 - r0);
-        for (int idx = lane; idx < ROWS * wb; idx += 32) {
-            const int rr = idx / wb, q = idx - rr * wb;
-            const int t = q < wl ? l0 + q : r0 + (q - wl);
-            const int sc = ext_index32(c_in0 + t, p.W, p.mode);
-            tile[rr * TILE_W + t] = sc >= 0 ? __ldg(xb + (int64_t)(rbase + rr) * p.x_rs + sc) : 0.f;
-        }
-        __syncwarp();
-    };
-    // ring write + detail stores of the level-1 row completed in slot S (compile-time), then the column extension
-    // of the approximation row in the edge strips
-#define WTB_WP_L1_OUT(S, STORE)                                                                                         \
-    {                                                                                                                   \
-        float* rrow = ring_lane + (produced & (RING - 1)) * RP;                                                          \
-        *reinterpret_cast<float4*>(rrow) = make_float4(acc1[S][0][0].x, acc1[S][0][0].y, acc1[S][0][1].x, acc1[S][0][1].y); \
-        if (STORE) {                                                                                                    \
-            *reinterpret_cast<float4*>(pd1) = make_float4(acc1[S][1][0].x, acc1[S][1][0].y, acc1[S][1][1].x, acc1[S][1][1].y); \
-            *reinterpret_cast<float4*>(pd1 + p.d1_band) =                                                               \
-                make_float4(acc1[S][2][0].x, acc1[S][2][0].y, acc1[S][2][1].x, acc1[S][2][1].y);                        \
-            *reinterpret_cast<float4*>(pd1 + 2 * p.d1_band) =                                                           \
-                make_float4(acc1[S][3][0].x, acc1[S][3][0].y, acc1[S][3][1].x, acc1[S][3][1].y);                        \
-        }                                                                                                               \
-        pd1 += p.d1_rs;                                                                                                 \
-        if (edge_a) {                                                                                                   \
-            __syncwarp();                                                                                               \
-            float* row0 = rrow - 4 * lane;                                                                              \
-            _Pragma("unroll") for (int jj = 0; jj < 4; ++jj)                                                            \
-                if (psrc[jj] != -2) rrow[jj] = psrc[jj] >= 0 ? row0[psrc[jj]] : 0.f;                                    \
-        }                                                                                                               \
-        ++produced;                                                                                                     \
-    }
-#define WTB_WP_L2_OUT(S, STORE)                                                                                         \
-    {                                                                                                                   \
-        if (STORE) {                                                                                                    \
-            *reinterpret_cast<float2*>(po2[0]) = acc2[S][0][0]; *reinterpret_cast<float2*>(po2[1]) = acc2[S][1][0];     \
-            *reinterpret_cast<float2*>(po2[2]) = acc2[S][2][0]; *reinterpret_cast<float2*>(po2[3]) = acc2[S][3][0];     \
-        }                                                                                                               \
-        _Pragma("unroll") for (int k = 0; k < 4; ++k) po2[k] += p.o2_rs[k];                                             \
-    }
-
-    int g = 0;
-    while (g < ngroups) {
-        // ================= fast blocks: FB groups of the steady state, every slot a compile-time constant ==========
-        {
-            const int rb = r_in0 + g * ROWS;
-            const int K2n = Y0 - (NA - 1) + j2;                // next level-2 pair
-            bool fast = rb >= 0 && rb + FB * ROWS <= p.H &&            // staged rows inside the image
-                        2 * g >= NA - 1 && 2 * (g + FB) <= n1 &&       // every step completes a row
-                        produced >= 2 * Y0 &&                          // every completed row is stored
-                        j2 >= NA - 1 && j2 + FB <= n2 &&               // every level-2 step completes a row
-                        K2n >= 0 && 2 * (K2n + FB) <= p.Mh1 &&         // level-2 sources inside the band ...
-                        (2 * K2n + 1 == produced || 2 * K2n + 1 == produced + 1);   // ... one pair per group
-            if (fast) {
-                wp_rotate<NA, 2>(acc1, s1);
-                wp_rotate<NA, 1>(acc2, s2);
-                s1 = 0; s2 = 0;
-                int l2row = 2 * K2n;
-                do {
+    for (int g0 = 0; g0 < ngroups; g0 += UNR) {
 #pragma unroll
-                    for (int u = 0; u < FB; ++u) {
-                        float* tile = s_tile + stage * STG_F;
-                        mbar_wait(&bars[stage], par);
-                        if (edge_in) patch_cols(tile, r_in0 + (g + u) * ROWS);
-                        const float* tl = tile_lane + stage * STG_F;
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            wp_l1_compute<L>(tl + (2 * h) * TILE_W, acc1, p, (2 * u + h) % NA);
-                            WTB_WP_L1_OUT((2 * u + h) % NA, store1)
-                        }
-                        __syncwarp();
-                        if (lane == 0 && g + u + NSTG < ngroups) {
-                            fence_proxy_async();
-                            mbar_expect_tx(&bars[stage], (uint32_t)Gm::STAGE_BYTES);
-                            tma_load_3d(tile, &tmap, &bars[stage], c_in0 / 2, r_in0 + (g + u + NSTG) * ROWS, b);
-                        }
-                        if (++stage == NSTG) { stage = 0; par ^= 1u; }
-                        wp_l2_compute<L>(ring_lane + (l2row & (RING - 1)) * RP, ring_lane + ((l2row + 1) & (RING - 1)) * RP,
-                                         acc2, p, u);
-                        WTB_WP_L2_OUT(u, store2)
-                        l2row += 2;
-                        __syncwarp();
-                    }
-                    g += FB;
-                    j2 += FB;
-                } while (r_in0 + (g + FB) * ROWS <= p.H && 2 * (g + FB) <= n1 && j2 + FB <= n2 &&
-                         l2row + 2 * FB <= p.Mh1);
-                continue;
-            }
-        }
-        // ================= generic group: prologue / epilogue / borders ================================================
-        {
+        for (int u = 0; u < UNR; ++u) {
+            const int g = g0 + u;
+            if (g >= ngroups) break;
             float* tile = s_tile + stage * STG_F;
             mbar_wait(&bars[stage], par);
             const int rbase = r_in0 + g * ROWS;
+
+            // ---- boundary extension of the staged input -------------------------------------------------
             if (need_patch) {
                 const bool rows_oob = rbase < 0 || rbase + ROWS > p.H;
                 if (rows_oob) {
@@ -398,55 +270,141 @@ fwd2d_wpair_kernel(const __grid_constant__ WPairParams p, const __grid_constant_
                     }
                     __syncwarp();
                 } else if (edge_in) {
-                    patch_cols(tile, rbase);
-                }
-            }
-            for (int h = 0; h < 2; ++h) {
-                const int j = 2 * g + h;
-                if (j < n1) {
-                    const float* tr = tile + (2 * h) * TILE_W + 8 * lane;
-                    const bool valid = j >= NA - 1;
-                    const bool st = store1 && produced >= 2 * Y0;
-                    switch (s1) {
-                        case 0: wp_l1_compute<L>(tr, acc1, p, 0); if (valid) WTB_WP_L1_OUT(0, st) break;
-                        case 1: if constexpr (NA > 1) { wp_l1_compute<L>(tr, acc1, p, (NA > 1 ? 1 : 0)); if (valid) WTB_WP_L1_OUT((NA > 1 ? 1 : 0), st) } break;
-                        case 2: if constexpr (NA > 2) { wp_l1_compute<L>(tr, acc1, p, (NA > 2 ? 2 : 0)); if (valid) WTB_WP_L1_OUT((NA > 2 ? 2 : 0), st) } break;
-                        default: if constexpr (NA > 3) { wp_l1_compute<L>(tr, acc1, p, (NA > 3 ? 3 : 0)); if (valid) WTB_WP_L1_OUT((NA > 3 ? 3 : 0), st) } break;
+                    // columns only: the L samples next to each border are all any valid output reads
+                    const int nl = c_in0 < 0 ? -c_in0 : 0;
+                    const int l0 = max(nl - L, 0);
+                    const int r0 = min(max(p.W - c_in0, 0), TILE_W), r1 = min(r0 + L, TILE_W);
+                    const int wl = nl - l0, wb = wl + (r1 - r0);
+                    for (int idx = lane; idx < ROWS * wb; idx += 32) {
+                        const int rr = idx / wb, q = idx - rr * wb;
+                        const int t = q < wl ? l0 + q : r0 + (q - wl);
+                        const int sc = ext_index32(c_in0 + t, p.W, p.mode);
+                        tile[rr * TILE_W + t] = sc >= 0 ? __ldg(xb + (int64_t)(rbase + rr) * p.x_rs + sc) : 0.f;
                     }
-                    s1 = s1 + 1 == NA ? 0 : s1 + 1;
+                    __syncwarp();
                 }
             }
-            __syncwarp();   // tile consumed by every lane; ring rows visible
+
+            // ---- level 1: two steps = one (even, odd) pair of approximation rows, straight-line code; accumulator
+            //      slots are compile-time constants, row validity only predicates the stores -------------------------
+            const int a0 = a_start + 2 * g - (NA - 1);             // rows completed by the two steps: a0 (even), a0 + 1
+            {
+                const int sl0 = (2 * u) % NA, sl1 = (2 * u + 1) % NA;
+                const float* tl = tile + 8 * lane;
+                wp_l1_compute<L>(tl, acc1, p, sl0);
+                const bool v0 = a0 >= a_lo && a0 < a_end;
+                const bool v1 = a0 + 1 >= a_lo && a0 + 1 < a_end;
+                float* rrow0 = row_lane + (a0 & 1) * RP1;
+                float* rrow1 = row_lane + ((a0 + 1) & 1) * RP1;
+                float* pdA = pd1 + (int64_t)(a0 - a_start) * p.d1_rs;
+                if (v0) {
+                    *reinterpret_cast<float4*>(rrow0) =
+                        make_float4(acc1[sl0][0][0].x, acc1[sl0][0][0].y, acc1[sl0][0][1].x, acc1[sl0][0][1].y);
+                    if (store1 && a0 >= 2 * Y0) {
+                        *reinterpret_cast<float4*>(pdA) =
+                            make_float4(acc1[sl0][1][0].x, acc1[sl0][1][0].y, acc1[sl0][1][1].x, acc1[sl0][1][1].y);
+                        *reinterpret_cast<float4*>(pdA + p.d1_band) =
+                            make_float4(acc1[sl0][2][0].x, acc1[sl0][2][0].y, acc1[sl0][2][1].x, acc1[sl0][2][1].y);
+                        *reinterpret_cast<float4*>(pdA + 2 * p.d1_band) =
+                            make_float4(acc1[sl0][3][0].x, acc1[sl0][3][0].y, acc1[sl0][3][1].x, acc1[sl0][3][1].y);
+                    }
+                }
+                wp_l1_compute<L>(tl + 2 * TILE_W, acc1, p, sl1);
+                if (v1) {
+                    *reinterpret_cast<float4*>(rrow1) =
+                        make_float4(acc1[sl1][0][0].x, acc1[sl1][0][0].y, acc1[sl1][0][1].x, acc1[sl1][0][1].y);
+                    if (store1 && a0 + 1 >= 2 * Y0) {
+                        float* pdB = pdA + p.d1_rs;
+                        *reinterpret_cast<float4*>(pdB) =
+                            make_float4(acc1[sl1][1][0].x, acc1[sl1][1][0].y, acc1[sl1][1][1].x, acc1[sl1][1][1].y);
+                        *reinterpret_cast<float4*>(pdB + p.d1_band) =
+                            make_float4(acc1[sl1][2][0].x, acc1[sl1][2][0].y, acc1[sl1][2][1].x, acc1[sl1][2][1].y);
+                        *reinterpret_cast<float4*>(pdB + 2 * p.d1_band) =
+                            make_float4(acc1[sl1][3][0].x, acc1[sl1][3][0].y, acc1[sl1][3][1].x, acc1[sl1][3][1].y);
+                    }
+                }
+                __syncwarp();
+                if (edge_a) {
+                    // boundary extension of the approximation band along the columns (edge strips)
+                    if (psrc[0] != -2 || psrc[3] != -2) {
+                        float* r0 = rrow0 - 4 * lane;
+                        float* r1 = rrow1 - 4 * lane;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (psrc[jj] != -2) {
+                                rrow0[jj] = psrc[jj] >= 0 ? r0[psrc[jj]] : 0.f;
+                                rrow1[jj] = psrc[jj] >= 0 ? r1[psrc[jj]] : 0.f;
+                            }
+                    }
+                    __syncwarp();
+                }
+                // level-2 row pass of both rows -> ring lines
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float* rrow = h ? rrow1 : rrow0;
+                    float w[4 * Gm::NV2_4];
+#pragma unroll
+                    for (int q = 0; q < Gm::NV2_4; ++q) {
+                        const float4 t = *reinterpret_cast<const float4*>(rrow + 4 * q);
+                        w[4 * q] = t.x; w[4 * q + 1] = t.y; w[4 * q + 2] = t.z; w[4 * q + 3] = t.w;
+                    }
+                    float l2[2], h2[2];
+                    wp_rowfilt<L, 2, Gm::OFF2>(w, p.pl, p.ph, l2, h2);
+                    if (h ? v1 : v0) {
+                        float* dst = ring_lane + ((a0 + h) & (RING - 1)) * R2P;
+                        *reinterpret_cast<float2*>(dst) = make_float2(l2[0], l2[1]);
+                        *reinterpret_cast<float2*>(dst + 64) = make_float2(h2[0], h2[1]);
+                    }
+                }
+                produced = min(max(a0 + 2, a_lo), a_end);
+            }
+            __syncwarp();   // tile consumed by every lane; ring lines visible
+
             if (lane == 0 && g + NSTG < ngroups) {
                 fence_proxy_async();
                 mbar_expect_tx(&bars[stage], (uint32_t)Gm::STAGE_BYTES);
                 tma_load_3d(tile, &tmap, &bars[stage], c_in0 / 2, r_in0 + (g + NSTG) * ROWS, b);
             }
             if (++stage == NSTG) { stage = 0; par ^= 1u; }
-            // level 2: every pair of approximation rows whose sources exist
-            while (j2 < n2) {
-                const int K2 = Y0 - (NA - 1) + j2;                     // output row this pair completes
-                int sA = 2 * K2, sB = 2 * K2 + 1;
-                if (sA < 0 || sB >= p.Mh1) { sA = ext_index32(sA, p.Mh1, p.mode); sB = ext_index32(sB, p.Mh1, p.mode); }
-                if (max(sA, sB) >= produced) break;
-                const float* rA = ring_lane + (sA < 0 ? RING : (sA & (RING - 1))) * RP;
-                const float* rB = ring_lane + (sB < 0 ? RING : (sB & (RING - 1))) * RP;
-                const bool valid = j2 >= NA - 1;
-                switch (s2) {
-                    case 0: wp_l2_compute<L>(rA, rB, acc2, p, 0); if (valid) WTB_WP_L2_OUT(0, store2) break;
-                    case 1: if constexpr (NA > 1) { wp_l2_compute<L>(rA, rB, acc2, p, (NA > 1 ? 1 : 0)); if (valid) WTB_WP_L2_OUT((NA > 1 ? 1 : 0), store2) } break;
-                    case 2: if constexpr (NA > 2) { wp_l2_compute<L>(rA, rB, acc2, p, (NA > 2 ? 2 : 0)); if (valid) WTB_WP_L2_OUT((NA > 2 ? 2 : 0), store2) } break;
-                    default: if constexpr (NA > 3) { wp_l2_compute<L>(rA, rB, acc2, p, (NA > 3 ? 3 : 0)); if (valid) WTB_WP_L2_OUT((NA > 3 ? 3 : 0), store2) } break;
+
+            // ---- level 2 column pass: every output row whose L ring lines exist ----------------------------
+            while (K2 < Y1) {
+                const int vb = 2 * K2 - HALO;                      // first row of the window
+                float2 o[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                if (vb >= 0 && vb + L <= p.Mh1) {
+                    if (vb + L > produced) break;
+#pragma unroll
+                    for (int j = 0; j < L; ++j) {
+                        const float* rr = ring_lane + ((vb + j) & (RING - 1)) * R2P;
+                        const float2 lo = *reinterpret_cast<const float2*>(rr), hi = *reinterpret_cast<const float2*>(rr + 64);
+                        o[0] = ffma2(p.vl[L - 1 - j], lo, o[0]); o[1] = ffma2(p.vl[L - 1 - j], hi, o[1]);
+                        o[2] = ffma2(p.vh[L - 1 - j], lo, o[2]); o[3] = ffma2(p.vh[L - 1 - j], hi, o[3]);
+                    }
+                } else {
+                    // window reaches over the top / bottom border of the approximation band
+                    int src[L], mx = -1;
+#pragma unroll
+                    for (int j = 0; j < L; ++j) { src[j] = ext_index32(vb + j, p.Mh1, p.mode); mx = max(mx, src[j]); }
+                    if (mx >= produced) break;
+#pragma unroll
+                    for (int j = 0; j < L; ++j) {
+                        if (src[j] < 0) continue;
+                        const float* rr = ring_lane + (src[j] & (RING - 1)) * R2P;
+                        const float2 lo = *reinterpret_cast<const float2*>(rr), hi = *reinterpret_cast<const float2*>(rr + 64);
+                        o[0] = ffma2(p.vl[L - 1 - j], lo, o[0]); o[1] = ffma2(p.vl[L - 1 - j], hi, o[1]);
+                        o[2] = ffma2(p.vh[L - 1 - j], lo, o[2]); o[3] = ffma2(p.vh[L - 1 - j], hi, o[3]);
+                    }
                 }
-                s2 = s2 + 1 == NA ? 0 : s2 + 1;
-                ++j2;
+                if (store2) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) *reinterpret_cast<float2*>(po2[k]) = o[k];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) po2[k] += p.o2_rs[k];
+                ++K2;
             }
-            __syncwarp();   // level-2 reads of the ring precede the next group's writes
-            ++g;
         }
     }
-#undef WTB_WP_L1_OUT
-#undef WTB_WP_L2_OUT
 }
 
 // ------------------------------------------------------------------------------------------
@@ -471,17 +429,17 @@ static bool make_tmap_3d_pairs(CUtensorMap* map, const float* base, int64_t B, i
 }
 
 // Returns true when the two levels were launched here (*err carries the launch status).
-template <int L>
+template <int L, int NSTG, int MINB>
 static bool launch_fwd2d_wpair_t(const float* x, int64_t B, int H, int W, int64_t x_bs, int64_t x_rs, const wt_level& l1,
                                  const wt_level& l2, int mode, const Taps<float>& taps, cudaStream_t st,
                                  uint64_t* launches, cudaError_t* err) {
-    using Gm = WPairGeom<L>;
+    using Gm = WPairGeom<L, NSTG>;
     WPairParams p;
     memset(&p, 0, sizeof(p));
     p.x = x; p.x_bs = x_bs; p.x_rs = x_rs; p.H = H; p.W = W;
     p.Mh1 = (int)l1.dims[0]; p.Mw1 = (int)l1.dims[1]; p.Mh2 = (int)l2.dims[0]; p.Mw2 = (int)l2.dims[1];
     if (mode == WT_MODE_PERIODIC) return false;
-    if (p.Mh1 < 2 * Gm::RING || p.Mw1 < 4 * L || p.Mh2 < L || p.Mw2 < L) return false;
+    if (p.Mh1 < 2 * Gm::RING + 2 || p.Mw1 < 4 * L || p.Mh2 < L || p.Mw2 < L) return false;
     // level-1 details: three bands with common strides, 128-bit stores
     p.d1 = (float*)l1.details; p.d1_bs = l1.details_batch_stride; p.d1_rs = l1.strides[0]; p.d1_band = l1.band_stride;
     if (l1.strides[1] != 1 || ((uintptr_t)p.d1 & 15) || (p.d1_bs & 3) || (p.d1_rs & 3) || (p.d1_band & 3) ||
@@ -539,7 +497,7 @@ static bool launch_fwd2d_wpair_t(const float* x, int64_t B, int H, int W, int64_
         p.nseg = n;
     }
     const int nseg = p.nseg;
-    auto kern = fwd2d_wpair_kernel<L>;
+    auto kern = fwd2d_wpair_kernel<L, NSTG, MINB>;
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM); });
@@ -566,12 +524,20 @@ template <>
 bool try_wpair<float>(const float* x, int64_t B, int H, int W, int64_t x_bs, int64_t x_rs, const wt_level& l1,
                       const wt_level& l2, int L, int mode, const Taps<float>& taps, cudaStream_t st,
                       uint64_t* launches, cudaError_t* err) {
-    if (knob_on(K_NO_WPAIR) || knob_on(K_DISABLE_FUSED)) return false;
+    // Opt-in (WTB200_WPAIR=1 / wt_set_knob("WPAIR", 1)): parity green, 19 % less DRAM traffic than one launch per level,
+    // but issue-bound (1.7 IPC/SM at 12 independent warps per SM) -- 1.84 ms vs 1.78-1.85 ms for the first two levels
+    // of 64 x 4096^2, i.e. no faster (profiles/r02_wpair_*).
+    if (!knob_on(K_WPAIR) || knob_on(K_NO_WPAIR) || knob_on(K_DISABLE_FUSED)) return false;
     switch (L) {
-        case 2: return launch_fwd2d_wpair_t<2>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
-        case 4: return launch_fwd2d_wpair_t<4>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
-        case 6: return launch_fwd2d_wpair_t<6>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
-        case 8: return launch_fwd2d_wpair_t<8>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
+        case 2: return launch_fwd2d_wpair_t<2, 3, 12>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
+        case 4: return launch_fwd2d_wpair_t<4, 3, 12>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
+        case 6: return launch_fwd2d_wpair_t<6, 3, 12>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
+        case 8:
+            if (knob_val(K_WPAIR_VAR, 0) == 1)
+                return launch_fwd2d_wpair_t<8, 2, 15>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
+            if (knob_val(K_WPAIR_VAR, 0) == 3)
+                return launch_fwd2d_wpair_t<8, 3, 12>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
+            return launch_fwd2d_wpair_t<8, 2, 12>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);
         default: return false;
     }
 }

@@ -37,6 +37,7 @@ def _cmp_every_image(got, x, wav, mode, level, what):
 @pytest.mark.parametrize("wav", ["haar", "db2", "db3", "db4", "sym4"])
 def test_wpair_kernel_every_mode_and_filter(knob, mode, wav):
     """Levels (1,2) and (3,4) through fwd2d_wpair_kernel (periodic falls back to one launch per level)."""
+    knob("WPAIR", 1)
     knob("WPAIR_MIN", 1)
     knob("WPAIR_DEEP", 1)
     g = torch.Generator().manual_seed(5)
@@ -56,6 +57,7 @@ def test_wpair_kernel_every_mode_and_filter(knob, mode, wav):
 @pytest.mark.parametrize("seg", [8, 13, 40])
 def test_wpair_segment_restarts(knob, seg):
     """Short row segments: every segment restarts both levels from its halo; the last one is ragged."""
+    knob("WPAIR", 1)
     knob("WPAIR_MIN", 1)
     knob("WPAIR_SEG", seg)
     g = torch.Generator().manual_seed(6 + seg)
@@ -70,6 +72,7 @@ def test_wpair_segment_restarts(knob, seg):
 
 def test_wpair_wide_and_narrow_strips(knob):
     """Strip layouts: one strip, many strips, a last strip of a few columns, a shifted last strip."""
+    knob("WPAIR", 1)
     knob("WPAIR_MIN", 1)
     g = torch.Generator().manual_seed(9)
     for w in (64, 120, 236, 240, 244, 248, 252, 484, 1000, 4096):
@@ -84,6 +87,7 @@ def test_chunked_two_stream_branch_small(knob, mode):
     """The branch the headline times (batch cut into chunks that alternate between the caller's stream and the
     library's auxiliary stream, scratch slots reused per stream), forced on small data: batch 7, chunks of 3."""
     knob("CHUNK", 3)
+    knob("WPAIR", 1)
     knob("WPAIR_MIN", 1)
     g = torch.Generator().manual_seed(31)
     for level in (2, 3, 4):
@@ -91,7 +95,7 @@ def test_chunked_two_stream_branch_small(knob, mode):
         got = wt.wavedec2(x.to(DEV), "db4", mode=mode, level=level)
         torch.cuda.synchronize()
         _cmp_every_image(got, x, "db4", mode, level, f"chunked {mode} L{level}")
-    with _native.knobs(NO_WPAIR=1):
+    with _native.knobs(WPAIR=0):
         x = torch.randn(7, 200, 264, generator=g)
         got = wt.wavedec2(x.to(DEV), "db4", mode=mode, level=3)
         _cmp_every_image(got, x, "db4", mode, 3, f"chunked per-level {mode}")
@@ -114,8 +118,9 @@ def test_headline_configuration_every_image():
     rec = wt.waverec2(c, "db4")
     err = (rec - x).abs().amax(dim=(1, 2))
     assert float(err.max()) < 2e-5 * float(x.abs().max()), f"round trip per image: {err.tolist()}"
-    # the per-level kernels must agree with the fused pair on the same data
-    with _native.knobs(NO_WPAIR=1):
+    del rec
+    # the opt-in two-level kernel must agree with the per-level kernels on the same data
+    with _native.knobs(WPAIR=1):
         c2 = flatten_coeffs(wt.wavedec2(x, "db4", level=4))
     scale = max(float(t.abs().max()) for t in c2)
     for j, (a, b) in enumerate(zip(flat, c2)):

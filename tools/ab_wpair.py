@@ -33,9 +33,10 @@ def main():
     res = {}
     for name, kn, lev in (
         ("default L4", {}, 4), ("per-level L4", {"NO_WPAIR": 1}, 4),
-        ("default L2", {}, 2), ("per-level L2", {"NO_WPAIR": 1}, 2),
-        ("seg64 L2", {"WPAIR_SEG": 64}, 2), ("seg96 L2", {"WPAIR_SEG": 96}, 2), ("seg200 L2", {"WPAIR_SEG": 200}, 2),
-        ("1 stream L4", {"STREAMS": 1}, 4), ("no chunk L4", {"CHUNK": 0}, 4),
+        ("var0 L2", {}, 2), ("var1 L2", {"WPAIR_VAR": 1}, 2), ("var2 L2", {"WPAIR_VAR": 2}, 2), ("per-level L2", {"NO_WPAIR": 1}, 2),
+        ("var1 L4", {"WPAIR_VAR": 1}, 4),
+        ("var1 seg96 L2", {"WPAIR_VAR": 1, "WPAIR_SEG": 96}, 2), ("var1 seg200 L2", {"WPAIR_VAR": 1, "WPAIR_SEG": 200}, 2),
+        ("var0 seg96 L2", {"WPAIR_SEG": 96}, 2), ("var0 seg200 L2", {"WPAIR_SEG": 200}, 2),
     ):
         with _native.knobs(**kn):
             _native.launch_count_reset()
