@@ -31,6 +31,13 @@
  *     device-pointer entry points, never synchronises the device, and keeps no
  *     reference to any argument after it returns.  Work is enqueued on `stream`
  *     (a cudaStream_t passed as void*).
+ *   - process-wide state the library DOES keep: (1) one auxiliary non-blocking stream and two events per
+ *     device, created on first use and never destroyed: large 2-D analyses (batch >= 16, >= 2^27 samples,
+ *     >= 2 levels) run the second half of the batch on it, forked from / joined back into `stream` with
+ *     those events, so the call still behaves as if everything ran in `stream` order (no host
+ *     synchronisation; disabled while `stream` is being captured into a CUDA graph, or with the switch
+ *     NO_AUX_STREAM); (2) the per-kernel dynamic shared-memory opt-in (set once per device and kernel);
+ *     (3) the launch counter and the tuning switches at the end of this header.
  *   - filter taps are HOST arrays of double in PyWavelets order (un-flipped dec_lo /
  *     dec_hi / rec_lo / rec_hi, reference src/ptwt/_util.py:95-126); they are rounded
  *     to the compute dtype inside and travel as kernel parameters, so concurrent
@@ -114,7 +121,10 @@ int wt_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * (general L: (n + padl + padr - L)/2 + 1 with the reference's pad amounts). */
 int64_t wt_coeff_len(int64_t n, int filt_len);
 
-/* Bytes of scratch wt_dwt_fwd / wt_dwt_inv need for the given problem (0 is possible). */
+/* Bytes of scratch wt_dwt_fwd / wt_dwt_inv need for the given problem (0 is possible: the fused kernels need
+ * none).  inverse: 0 analysis, 1 synthesis; bit 1 set (2, 3) asks for the requirement of the GENERAL path whatever a
+ * fused kernel covers -- a fused kernel can still decline at launch time (layouts it does not handle); the transform
+ * then returns WT_EWORKSPACE and the caller retries with this amount. */
 size_t wt_dwt_workspace_bytes(int ndim, int dtype, int levels, int filt_len, int64_t batch,
                               const int64_t* dims, int inverse);
 

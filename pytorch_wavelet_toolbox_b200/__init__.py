@@ -21,7 +21,7 @@ from .constants import (
     WaveletDetailTuple2d,
     WaveletTensorTuple,
 )
-from .fwt import wavedec, wavedec2, wavedec3, waverec, waverec2, waverec3
+from .fwt import host_staging, wavedec, wavedec2, wavedec3, waverec, waverec2, waverec3
 from .matrix_fwt import MatrixWavedec, MatrixWaverec, construct_boundary_a, construct_boundary_s
 from .matrix_fwt_nd import MatrixWavedec2, MatrixWavedec3, MatrixWaverec2, MatrixWaverec3
 from .separable import fswavedec2, fswavedec3, fswaverec2, fswaverec3
@@ -39,7 +39,7 @@ NEXT_ROW_NAMES = (
 
 __all__ = list(HOT_PATH_NAMES) + list(NEXT_ROW_NAMES) + [
     "Wavelet", "WaveletTensorTuple", "WaveletDetailTuple2d", "WaveletDetailDict", "WaveletCoeff1d",
-    "WaveletCoeff2d", "WaveletCoeffNd", "construct_boundary_a", "construct_boundary_s", "install", "uninstall",
+    "WaveletCoeff2d", "WaveletCoeffNd", "construct_boundary_a", "construct_boundary_s", "install", "uninstall", "host_staging",
 ]
 
 _saved: dict = {}

@@ -19,6 +19,7 @@ LIB_PATH = _HERE / "csrc" / "libwtb200.so"
 WT_F32, WT_F64 = 0, 1
 MODES = {"zero": 0, "constant": 1, "reflect": 2, "periodic": 3, "symmetric": 4}
 WT_MAX_FILT_LEN = 128
+WT_EWORKSPACE = -3
 
 _i64 = C.c_int64
 _i64p = C.POINTER(C.c_int64)

@@ -205,8 +205,7 @@ static bool launch_conv1d_fused(int L, int k, const int64_t* n, int mode, const 
     dim3 grid((nk + tk - 1) / tk, (unsigned)batch);
 #define WTB_CF(LL)                                                                                              \
     case LL: {                                                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(conv1d_fused_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem);                                                        \
+        cudaError_t e = ensure_dyn_smem(conv1d_fused_kernel<T, LL>, smem > 200 * 1024 ? smem : 200 * 1024);          \
         if (e != cudaSuccess) { *err = e; return true; }                                                        \
         conv1d_fused_kernel<T, LL><<<grid, 256, smem, st>>>(p);                                                 \
         break;                                                                                                  \

@@ -7,7 +7,31 @@
 #include "../../include/wtb200.h"
 #include "knobs.cuh"
 
+#include <mutex>
+#include <unordered_map>
+
 namespace wtb {
+
+// Opt a kernel in to `bytes` of dynamic shared memory.  cudaFuncSetAttribute is a driver call whose cost is far from
+// negligible when the value CHANGES from launch to launch (measured: ~1.3 ms per change, 4 ms of host time per
+// MatrixWavedec call in round 1), so the limit is only ever raised, once per (device, kernel), and kernels whose
+// need varies with the problem ask for their maximum up front.
+template <typename K>
+static cudaError_t ensure_dyn_smem(K kern, size_t bytes) {
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, size_t> cur;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const uint64_t key = (uint64_t)(uintptr_t)kern * 64u + (uint64_t)(dev & 63);
+    std::lock_guard<std::mutex> g(mu);
+    size_t& v = cur[key];
+    if (bytes <= v) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) v = bytes;
+    return e;
+}
+constexpr size_t WTB_MAX_DYN_SMEM = 227 * 1024;
+
 
 // Filter taps travel as kernel parameters (no __constant__ symbols), so concurrent
 // streams may run different wavelets.

@@ -689,7 +689,7 @@ static cudaError_t launch_fwd2d_level(const T* x, int64_t B, int H, int W, int64
             smem = Fwd2dGeomF<L, TW>::SMEM;
         }
     }
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dyn_smem(kern, smem);
     if (e != cudaSuccess) return e;
     const int nstrip = (Mw + TW - 1) / TW;
     for (int64_t b0 = 0; b0 < B; b0 += 65535) {
@@ -745,15 +745,26 @@ static bool fused2d_fwd_covers(int ndim, int L) {
 // under the bandwidth-bound level-1 launch of the next (fork / join with events; no host sync).
 struct AuxStream {
     cudaStream_t s = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;   // created once per device, reused by every call
+    std::mutex mu;                                // orders the record / wait pairs of concurrent callers
 };
-static cudaStream_t aux_stream_for_current_device() {
+static AuxStream* aux_stream_for_current_device() {
     static std::mutex mu;
     static AuxStream aux[64];
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> g(mu);
-    if (!aux[dev].s && cudaStreamCreateWithFlags(&aux[dev].s, cudaStreamNonBlocking) != cudaSuccess) aux[dev].s = nullptr;
-    return aux[dev].s;
+    AuxStream& a = aux[dev];
+    if (!a.s) {
+        if (cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) != cudaSuccess) { a.s = nullptr; return nullptr; }
+        if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamDestroy(a.s);
+            a.s = nullptr;
+            return nullptr;
+        }
+    }
+    return &a;
 }
 
 template <typename T>
@@ -787,16 +798,16 @@ static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* 
     }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (nstreams > 1 && (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)) nstreams = 1;
-    cudaStream_t s2 = nstreams > 1 ? aux_stream_for_current_device() : nullptr;
+    if (knob_on(K_NO_AUX_STREAM)) nstreams = 1;
+    AuxStream* aux = nstreams > 1 ? aux_stream_for_current_device() : nullptr;
+    cudaStream_t s2 = aux ? aux->s : nullptr;
     if (!s2) nstreams = 1;
     if (chunk <= 0 || chunk >= batch || levels > 32)
         return fused2d_fwd_run<T>(ndim, mode, levels, L, dlo, dhi, x, batch, dims, xs, xbs, lv, st, first_generic);
-    cudaEvent_t fork = nullptr, join = nullptr;
     if (nstreams > 1) {
-        if (cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) != cudaSuccess) return cuda_fail(cudaGetLastError(), "event");
-        if (cudaEventCreateWithFlags(&join, cudaEventDisableTiming) != cudaSuccess) { cudaEventDestroy(fork); return cuda_fail(cudaGetLastError(), "event"); }
-        cudaEventRecord(fork, st);
-        cudaStreamWaitEvent(s2, fork, 0);
+        std::lock_guard<std::mutex> g(aux->mu);
+        cudaEventRecord(aux->fork, st);
+        cudaStreamWaitEvent(s2, aux->fork, 0);
     }
     int rc = 0, fg = levels;
     wt_level sub[32];
@@ -829,10 +840,9 @@ static int fused2d_fwd_try(int ndim, int mode, int levels, int L, const double* 
         }
     }
     if (nstreams > 1) {
-        cudaEventRecord(join, s2);
-        cudaStreamWaitEvent(st, join, 0);
-        cudaEventDestroy(fork);
-        cudaEventDestroy(join);
+        std::lock_guard<std::mutex> g(aux->mu);
+        cudaEventRecord(aux->join, s2);
+        cudaStreamWaitEvent(st, aux->join, 0);
     }
     *first_generic = fg;
     return rc;

@@ -385,7 +385,7 @@ static int launch_fwd2d_mega(int mode, int levels, const double* dlo, const doub
     const bool hints = !knob_on(K_MEGA_NOHINTS);
     auto kern = hints ? fwd2d_mega_kernel<L, true> : fwd2d_mega_kernel<L, false>;
     const size_t smem = Fwd2dGeomF<L, 64>::SMEM;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = ensure_dyn_smem(kern, smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
     int dev = 0, sms = 148, occ = 0;
     cudaGetDevice(&dev);

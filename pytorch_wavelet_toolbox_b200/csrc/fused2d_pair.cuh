@@ -445,7 +445,7 @@ static cudaError_t launch_fwd2d_pair_t(const float* x, int64_t B, int H, int W, 
     memset(&tmap, 0, sizeof(tmap));
     const bool tma = make_tmap_3d<float>(&tmap, x, B, H, W, x_bs, x_rs, Gm::SW1, Gm::IN_ROWS);
     auto kern = tma ? fwd2d_pair_kernel<L, true, TW2_> : fwd2d_pair_kernel<L, false, TW2_>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+    cudaError_t e = ensure_dyn_smem(kern, (size_t)Gm::SMEM);
     if (e != cudaSuccess) return e;
     const int nstrip = (p.Mw2 + Gm::TW2 - 1) / Gm::TW2;
     for (int64_t b0 = 0; b0 < B; b0 += 65535) {

@@ -498,9 +498,7 @@ static bool launch_fwd2d_wpair_t(const float* x, int64_t B, int H, int W, int64_
     }
     const int nseg = p.nseg;
     auto kern = fwd2d_wpair_kernel<L, NSTG, MINB>;
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [&] { attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM); });
+    const cudaError_t attr_err = ensure_dyn_smem(kern, (size_t)Gm::SMEM);
     if (attr_err != cudaSuccess) { *err = attr_err; return true; }
     *err = cudaSuccess;
     for (int64_t b0 = 0; b0 < B; b0 += 65535) {

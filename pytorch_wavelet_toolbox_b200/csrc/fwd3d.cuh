@@ -306,7 +306,7 @@ static cudaError_t launch_fwd3d_tiles(Fwd3dParams& p, const float* x, int64_t B,
     memset(&tmap, 0, sizeof(tmap));
     const bool tma = make_tmap_4d(&tmap, x, B, D, H, W, x_bs, x_ps, x_rs, Gm::SW, Gm::ROWS);
     auto kern = tma ? fwd3d_tile_kernel<L, TH, TW, true> : fwd3d_tile_kernel<L, TH, TW, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+    cudaError_t e = ensure_dyn_smem(kern, (size_t)Gm::SMEM);
     if (e != cudaSuccess) return e;
     dim3 grid(ntx, nty * nseg, (unsigned)B);
     kern<<<grid, Gm::NT, Gm::SMEM, st>>>(p, tmap);

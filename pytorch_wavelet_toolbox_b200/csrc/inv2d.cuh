@@ -260,7 +260,7 @@ static cudaError_t launch_inv2d_level(const float* const in[4], const int64_t in
     nseg = (OH + seg - 1) / seg;
     p.seg_rows = seg;
     auto kern = tma ? inv2d_strip_kernel<L, true> : inv2d_strip_kernel<L, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+    cudaError_t e = ensure_dyn_smem(kern, (size_t)Gm::SMEM);
     if (e != cudaSuccess) return e;
     for (int64_t b0 = 0; b0 < B; b0 += 65535) {
         p.batch0 = (int)b0;

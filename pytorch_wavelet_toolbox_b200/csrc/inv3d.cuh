@@ -275,7 +275,7 @@ static cudaError_t launch_inv3d_level(const wt_level& d, int64_t B, float* y, in
     p.nty = nty;
     if ((int64_t)nty * nseg > 65535 || B > 65535) return cudaErrorInvalidConfiguration;
     auto kern = tma ? inv3d_tile_kernel<L, true> : inv3d_tile_kernel<L, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm::SMEM);
+    cudaError_t e = ensure_dyn_smem(kern, (size_t)Gm::SMEM);
     if (e != cudaSuccess) return e;
     dim3 grid(ntx, nty * nseg, (unsigned)B);
     kern<<<grid, Gm::NT, Gm::SMEM, st>>>(p, maps);

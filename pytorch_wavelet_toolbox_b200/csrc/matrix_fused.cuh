@@ -253,8 +253,7 @@ static bool launch_mat_fwd_fused(int L, int k, const int64_t* n, const int32_t* 
     dim3 grid((nk + tk - 1) / tk, (unsigned)batch);
 #define WTB_MF(LL)                                                                                              \
     case LL: {                                                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(mat_fwd_fused_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem);                                                        \
+        cudaError_t e = ensure_dyn_smem(mat_fwd_fused_kernel<T, LL>, smem > 200 * 1024 ? smem : 200 * 1024);         \
         if (e != cudaSuccess) { *err = e; return true; }                                                        \
         mat_fwd_fused_kernel<T, LL><<<grid, 256, smem, st>>>(p);                                                \
         break;                                                                                                  \
@@ -478,8 +477,7 @@ static bool launch_mat_inv_fused(int L, int k, const int64_t* n, int64_t keep0, 
     dim3 grid((unsigned)((keep0 + chunk - 1) / chunk), (unsigned)batch);
 #define WTB_MIF(LL)                                                                                             \
     case LL: {                                                                                                  \
-        cudaError_t e = cudaFuncSetAttribute(mat_inv_fused_kernel<T, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem);                                                        \
+        cudaError_t e = ensure_dyn_smem(mat_inv_fused_kernel<T, LL>, smem > 200 * 1024 ? smem : 200 * 1024);         \
         if (e != cudaSuccess) { *err = e; return true; }                                                        \
         mat_inv_fused_kernel<T, LL><<<grid, 256, smem, st>>>(p);                                                \
         break;                                                                                                  \

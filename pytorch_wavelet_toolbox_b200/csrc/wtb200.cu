@@ -124,30 +124,43 @@ static cudaError_t launch_axis_inv(const View<const T>& lo, const View<const T>&
     return cudaGetLastError();
 }
 
-// Scratch layout of the general (one launch per axis pass) path, in elements.
-static void generic_scratch_elems(int ndim, int L, int64_t batch, const int64_t* dims, int inverse,
+// Scratch of the general (one launch per axis pass) path, in elements: the per-level temporaries of the LARGEST
+// level.  Extents can grow from level to level (an explicit `levels` beyond dwt_max_level on an axis shorter than
+// L - 2: n -> floor((n + L - 1) / 2) > n), so every level is walked.
+//   analysis, level input [H, W] / [D, H, W] with coefficient extents M*:
+//     2-D: 2 * batch * H * Mw                      3-D: 2 * batch * D * H * Mw + 4 * batch * D * Mh * Mw
+//   synthesis, level output [OH, OW] / [OD, OH, OW] from coefficient extents M* (upper bounds: the output of a level
+//   may be one sample longer than the next finer coefficient extent):
+//     2-D: 2 * batch * OH * Mw                     3-D: 4 * batch * OD * Mh * Mw + 2 * batch * OD * OH * Mw
+static void generic_scratch_elems(int ndim, int L, int levels, int64_t batch, const int64_t* dims, int inverse,
                                   int64_t* s1, int64_t* s2) {
     *s1 = 0; *s2 = 0;
     if (ndim == 1) return;
-    if (!inverse) {
-        if (ndim == 2) {
-            *s1 = 2 * batch * dims[0] * coeff_len(dims[1], L);
+    int64_t cur[3] = {1, 1, 1};
+    for (int a = 0; a < ndim; ++a) cur[a] = dims[a];
+    int64_t best = -1;
+    for (int l = 0; l < (levels > 0 ? levels : 1); ++l) {
+        int64_t a1 = 0, a2 = 0, c[3] = {1, 1, 1};
+        if (!inverse) {
+            for (int a = 0; a < ndim; ++a) c[a] = coeff_len(cur[a], L);
+            if (ndim == 2) {
+                a1 = 2 * batch * cur[0] * c[1];
+            } else {
+                a1 = 2 * batch * cur[0] * cur[1] * c[2];
+                a2 = 4 * batch * cur[0] * c[1] * c[2];
+            }
         } else {
-            *s1 = 2 * batch * dims[0] * dims[1] * coeff_len(dims[2], L);
-            *s2 = 4 * batch * dims[0] * coeff_len(dims[1], L) * coeff_len(dims[2], L);
+            int64_t full[3] = {1, 1, 1};
+            for (int a = 0; a < ndim; ++a) { c[a] = coeff_len(cur[a] + (cur[a] & 1), L) + 1; full[a] = cur[a] + 1; }
+            if (ndim == 2) {
+                a1 = 2 * batch * full[0] * c[1];
+            } else {
+                a1 = 4 * batch * full[0] * c[1] * c[2];
+                a2 = 2 * batch * full[0] * full[1] * c[2];
+            }
         }
-    } else {
-        // dims = extents of the finest reconstruction (upper bound for every level)
-        int64_t c[3];
-        for (int a = 0; a < ndim; ++a) c[a] = coeff_len(dims[a] + (dims[a] & 1), L) + 1;
-        int64_t full[3];
-        for (int a = 0; a < ndim; ++a) full[a] = dims[a] + 1;
-        if (ndim == 2) {
-            *s1 = 2 * batch * full[0] * c[1];
-        } else {
-            *s1 = 4 * batch * full[0] * c[1] * c[2];
-            *s2 = 2 * batch * full[0] * full[1] * c[2];
-        }
+        if (a1 + a2 > best) { best = a1 + a2; *s1 = a1; *s2 = a2; }
+        for (int a = 0; a < ndim; ++a) cur[a] = c[a];
     }
 }
 
@@ -434,7 +447,7 @@ static int dwt_fwd_t(int ndim, int mode, int levels, int L, const double* dlo, c
         if (!lv[l].details || !lv[l].approx) return fail(WT_EINVAL, "level %d: NULL buffer", l + 1);
     }
     int64_t s1, s2;
-    generic_scratch_elems(ndim, L, batch, dims, 0, &s1, &s2);
+    generic_scratch_elems(ndim, L, levels, batch, dims, 0, &s1, &s2);
     int first_generic = 0;
 #ifndef WTB_NO_FUSED
     if constexpr (sizeof(T) == 4) {
@@ -502,7 +515,7 @@ static int dwt_inv_t(int ndim, int levels, int L, const double* rlo, const doubl
     }
 #endif
     int64_t s1, s2;
-    generic_scratch_elems(ndim, L, batch, out_dims, 1, &s1, &s2);
+    generic_scratch_elems(ndim, L, levels, batch, out_dims, 1, &s1, &s2);
     if (ndim > 1 && levels > 0 && ((size_t)(s1 + s2) * sizeof(T) > ws_bytes || !ws))
         return fail(WT_EWORKSPACE, "workspace: need %zu bytes, have %zu", (size_t)(s1 + s2) * sizeof(T), ws_bytes);
     return dwt_inv_generic<T>(ndim, levels, L, taps, (T*)y, batch, out_dims, ys, ybs, lv, 0, (T*)ws, st);
@@ -815,19 +828,23 @@ int64_t wt_coeff_len(int64_t n, int filt_len) { return coeff_len(n, filt_len); }
 size_t wt_dwt_workspace_bytes(int ndim, int dtype, int levels, int filt_len, int64_t batch, const int64_t* dims,
                               int inverse) {
     if (ndim < 1 || ndim > 3 || !dims || levels <= 0) return 0;
+    const bool general = (inverse & 2) != 0;   // bit 1: the requirement of the general path, whatever a fused path covers
+    inverse &= 1;
 #ifndef WTB_NO_FUSED
-    if (!inverse && fused2d_fwd_covers(ndim, filt_len)) {
+    if (general) {
+        // fall through to the general requirement
+    } else if (!inverse && fused2d_fwd_covers(ndim, filt_len)) {
         // the fused path needs no scratch unless it has to bail out (odd strides); keep the
         // general path's requirement only when the fused path is disabled.  The persistent multi-level
         // kernel keeps its work-queue and completion counters in the workspace.
         return (dtype == WT_F32 && mega2d_enabled()) ? mega_workspace_bytes(levels, batch) : 0;
     }
-    if (inverse && fused2d_inv_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len)) return 0;
-    if (!inverse && fused3d_fwd_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len) && batch <= 65535) return 0;
-    if (inverse && fused3d_inv_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len) && batch <= 65535) return 0;
+    else if (inverse && fused2d_inv_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len)) return 0;
+    else if (!inverse && fused3d_fwd_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len) && batch <= 65535) return 0;
+    else if (inverse && fused3d_inv_covers(ndim, dtype == WT_F64 ? 8 : 4, filt_len) && batch <= 65535) return 0;
 #endif
     int64_t s1, s2;
-    generic_scratch_elems(ndim, filt_len, batch, dims, inverse, &s1, &s2);
+    generic_scratch_elems(ndim, filt_len, levels, batch, dims, inverse, &s1, &s2);
     return (size_t)(s1 + s2) * (dtype == WT_F64 ? 8 : 4);
 }
 

@@ -235,12 +235,53 @@ def _analysis(data: torch.Tensor, wavelet: Any, mode: Optional[str], level: Opti
         scratch = torch.empty((batch, max(scratch_elems, 1)), dtype=x.dtype, device=dev)
         _run_fwd(xd, plan, mode, dec_lo, dec_hi, buf, scratch)
         if on_host:
-            host = torch.empty(buf.shape, dtype=buf.dtype, pin_memory=True)
+            host = pinned_empty(buf.shape, buf.dtype)
             host.copy_(buf, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             buf = host
     approx, details = _result_views(buf, plan)
     return approx, details, f
+
+
+# --------------------------------------------------------------------------------------
+# host staging: CPU tensors in -> pinned result out
+# --------------------------------------------------------------------------------------
+_host_reuse = False
+_host_cache: dict = {}
+
+
+class host_staging:
+    """``with host_staging(reuse=True): ...`` -- results of transforms of CPU tensors are written into ONE pinned host
+    buffer per (shape, dtype) that is REUSED by the next call of the same shape (page-locking 4 GB per call costs more
+    than the transform).  The tensors returned by a call are then only valid until the next call of that shape; the
+    default (``reuse=False``) gives every call a fresh pinned buffer like round 1.  The cache is dropped on exit."""
+
+    def __init__(self, reuse: bool = True):
+        self.reuse = reuse
+
+    def __enter__(self):
+        global _host_reuse
+        self._old = _host_reuse
+        _host_reuse = self.reuse
+        return self
+
+    def __exit__(self, *exc):
+        global _host_reuse
+        _host_reuse = self._old
+        if not _host_reuse:
+            _host_cache.clear()
+        return False
+
+
+def pinned_empty(shape, dtype: torch.dtype) -> torch.Tensor:
+    """Pinned host buffer for a result (fresh, or the cached one inside ``host_staging(reuse=True)``)."""
+    if not _host_reuse:
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+    key = (tuple(shape), dtype)
+    buf = _host_cache.get(key)
+    if buf is None:
+        buf = _host_cache[key] = torch.empty(shape, dtype=dtype, pin_memory=True)
+    return buf
 
 
 #: host inputs at least this large are transformed through the chunked copy/compute/copy pipeline
@@ -262,7 +303,7 @@ def _analysis_host_pipeline(x: torch.Tensor, plan: _Plan, mode: str, dec_lo, dec
             _pipe_streams[dev] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
         s_in, s_cmp, s_out = _pipe_streams[dev]
         xs = x if x.is_contiguous() else x.contiguous()
-        host = torch.empty((batch, plan.item_elems), dtype=x.dtype, pin_memory=True)
+        host = pinned_empty((batch, plan.item_elems), x.dtype)
         d_in = [torch.empty((bc,) + tuple(x.shape[1:]), dtype=x.dtype, device=dev) for _ in range(2)]
         d_out = [torch.empty((bc, plan.item_elems), dtype=x.dtype, device=dev) for _ in range(2)]
         scratch = torch.empty((bc, max(sum(lv.plane for lv in plan.levels[:-1]), 1)), dtype=x.dtype, device=dev)
@@ -354,6 +395,18 @@ def _taps_c(seq, dt: torch.dtype):
     return _taps_c_cached(tuple(float(v) for v in seq), dt)
 
 
+def _unit_strides(t: torch.Tensor) -> list[int]:
+    """Element strides with the (arbitrary) strides of size-1 axes replaced by the contiguous value, so that a
+    size-1 last axis never looks like a strided innermost axis to the native code."""
+    st = list(t.stride())
+    nxt = 1
+    for a in range(t.dim() - 1, -1, -1):
+        if t.shape[a] == 1:
+            st[a] = nxt
+        nxt = st[a] * t.shape[a] if t.shape[a] > 1 else nxt
+    return st
+
+
 def _run_fwd(xd: torch.Tensor, plan: _Plan, mode: str, dec_lo, dec_hi, buf: torch.Tensor,
              scratch: torch.Tensor) -> None:
     lib = N.load()
@@ -362,17 +415,20 @@ def _run_fwd(xd: torch.Tensor, plan: _Plan, mode: str, dec_lo, dec_hi, buf: torc
     lo_arr, lo_p = _taps_c(dec_lo, dt)
     hi_arr, hi_p = _taps_c(dec_hi, dt)
     dims_arr, dims_p = plan.dims_c
-    xs_arr, xs_p = N.i64_array(xd.stride()[1:])
+    xs_arr, xs_p = N.i64_array(_unit_strides(xd)[1:])
     levels = _fill_levels(plan, buf, scratch)
     code = _dtype_code(dt)
-    ws_bytes = int(lib.wt_dwt_workspace_bytes(plan.ndim, code, len(plan.levels), plan.filt_len, batch, dims_p, 0))
-    ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=xd.device) if ws_bytes else None
     stream = torch.cuda.current_stream(xd.device).cuda_stream
-    rc = lib.wt_dwt_fwd(
-        plan.ndim, code, N.MODES[mode], len(plan.levels), plan.filt_len, lo_p, hi_p,
-        xd.data_ptr(), batch, dims_p, xs_p, xd.stride(0), levels,
-        ws.data_ptr() if ws is not None else None, ws_bytes, stream,
-    )
+    for general in (0, 2):
+        ws_bytes = int(lib.wt_dwt_workspace_bytes(plan.ndim, code, len(plan.levels), plan.filt_len, batch, dims_p, general))
+        ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=xd.device) if ws_bytes else None
+        rc = lib.wt_dwt_fwd(
+            plan.ndim, code, N.MODES[mode], len(plan.levels), plan.filt_len, lo_p, hi_p,
+            xd.data_ptr(), batch, dims_p, xs_p, xd.stride(0), levels,
+            ws.data_ptr() if ws is not None else None, ws_bytes, stream,
+        )
+        if rc != N.WT_EWORKSPACE:
+            break   # a fused kernel declined at launch time: once more with the general path's scratch
     N.check(rc, "wt_dwt_fwd")
 
 
@@ -531,14 +587,17 @@ def _synthesis(approx: torch.Tensor, levels_in: list[list[torch.Tensor]], probes
         od_arr, od_p = N.i64_array(out_dims)
         ys_arr, ys_p = N.i64_array(y.stride()[1:])
         code = _dtype_code(dt)
-        ws_bytes = int(lib.wt_dwt_workspace_bytes(ndim, code, nl, filt_len, batch, od_p, 1))
-        ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev) if ws_bytes else None
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.wt_dwt_inv(ndim, code, nl, filt_len, lo_p, hi_p, y.data_ptr(), batch, od_p, ys_p, y.stride(0),
-                            arr, ws.data_ptr() if ws is not None else None, ws_bytes, stream)
+        for general in (1, 3):
+            ws_bytes = int(lib.wt_dwt_workspace_bytes(ndim, code, nl, filt_len, batch, od_p, general))
+            ws = torch.empty((max(ws_bytes, 1),), dtype=torch.uint8, device=dev) if ws_bytes else None
+            rc = lib.wt_dwt_inv(ndim, code, nl, filt_len, lo_p, hi_p, y.data_ptr(), batch, od_p, ys_p, y.stride(0),
+                                arr, ws.data_ptr() if ws is not None else None, ws_bytes, stream)
+            if rc != N.WT_EWORKSPACE:
+                break   # a fused kernel declined at launch time: once more with the general path's scratch
         N.check(rc, "wt_dwt_inv")
         if on_host:
-            host = torch.empty(y.shape, dtype=dt, pin_memory=True)
+            host = pinned_empty(y.shape, dt)
             host.copy_(y, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             y = host

@@ -27,7 +27,7 @@ import torch
 from . import _native as N
 from ._shape import AxisHint, Fold, check_dtype, check_mode, check_tensor, ensure_axes, fold, unfold
 from ._wavelets import as_wavelet, filter_bank, taps_in_dtype
-from .fwt import _compute_device, _dtype_code, _no_autograd, _same_device_dtype
+from .fwt import _compute_device, _dtype_code, _no_autograd, _same_device_dtype, pinned_empty
 
 __all__ = ["MatrixWavedec", "MatrixWaverec", "construct_boundary_a", "construct_boundary_s", "orthogonalize_rows"]
 
@@ -463,7 +463,7 @@ class MatrixWavedec:
             )
             N.check(rc, "wt_matrix_fwd")
             if on_host:
-                host = torch.empty(out.shape, dtype=dt, pin_memory=True)
+                host = pinned_empty(out.shape, dt)
                 host.copy_(out, non_blocking=True)
                 torch.cuda.current_stream(dev).synchronize()
                 out = host
@@ -613,7 +613,7 @@ class MatrixWaverec:
             )
             N.check(rc, "wt_matrix_inv")
             if on_host:
-                host = torch.empty(y.shape, dtype=dt, pin_memory=True)
+                host = pinned_empty(y.shape, dt)
                 host.copy_(y, non_blocking=True)
                 torch.cuda.current_stream(dev).synchronize()
                 y = host

@@ -15,7 +15,7 @@ import torch
 
 from .constants import DETAIL_KEYS_3D, WaveletDetailTuple2d
 
-__all__ = ["shard_bounds", "shard", "pack_coeffs", "unpack_coeffs", "all_gather_coeffs"]
+__all__ = ["shard_bounds", "shard", "pack_coeffs", "unpack_coeffs", "all_gather_coeffs", "transform_and_gather"]
 
 
 def shard_bounds(n: int, world: int) -> list[tuple[int, int]]:
@@ -80,23 +80,109 @@ def unpack_coeffs(flat: torch.Tensor, meta: dict):
     return out if meta["list"] else tuple(out)
 
 
-def all_gather_coeffs(coeffs, total_batch: int, group=None):
-    """Collect the shards of all ranks with ONE all_gather of the packed buffers.
+def _packed_base(tensors: Sequence[torch.Tensor]) -> Optional[torch.Tensor]:
+    """The ONE ``[B, P]`` buffer the transforms of this package return views of (``fwt._make_plan``: every band a dense
+    block inside a per-item record of P elements), or None for any other layout."""
+    t0 = tensors[0]
+    base = t0._base
+    if base is None or base.dim() != 2 or not base.is_contiguous() or base.storage_offset() != 0:
+        return None
+    ptr = base.untyped_storage().data_ptr()
+    for t in tensors:
+        if t.dim() < 1 or t.shape[0] != base.shape[0] or t.untyped_storage().data_ptr() != ptr:
+            return None
+        if t.numel() and t.shape[0] > 1 and t.stride(0) != base.stride(0):
+            return None
+    return base
 
-    ``total_batch`` is the global batch size; shards follow :func:`shard_bounds`.  Uneven shards are
-    padded to the largest one for the collective and trimmed afterwards.
+
+def _rebuild(coeffs, fn):
+    """Same pytree with every tensor replaced by fn(tensor)."""
+    out: list[Any] = []
+    for el in coeffs:
+        if isinstance(el, torch.Tensor):
+            out.append(fn(el))
+        elif isinstance(el, dict):
+            out.append({k: fn(v) for k, v in el.items()})
+        else:
+            out.append(type(el)(*[fn(v) for v in el]) if hasattr(el, "_fields") else type(el)(fn(v) for v in el))
+    return out if isinstance(coeffs, list) else tuple(out)
+
+
+def all_gather_coeffs(coeffs, total_batch: int, group=None):
+    """Collect the shards of all ranks with ONE all_gather.
+
+    ``total_batch`` is the global batch size; shards follow :func:`shard_bounds`.  The coefficient tensors this package
+    returns are views of one packed ``[B_local, P]`` buffer per call, identical in layout on every rank: that buffer IS
+    the message (no packing copy), and the result is the same pytree of views over the gathered ``[B_total, P]``
+    buffer.  Foreign layouts and uneven shards are packed (``pack_coeffs``) and, if uneven, padded to the largest
+    shard for the collective and trimmed afterwards.
     """
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     bounds = shard_bounds(total_batch, world)
     bmax = max(hi - lo for lo, hi in bounds)
+    even = all(hi - lo == bmax for lo, hi in bounds)
+    tensors, _ = _flatten(coeffs)
+    base = _packed_base(tensors) if even else None
+    if base is not None and base.shape[0] == bmax:
+        p = base.shape[1]
+        out = torch.empty((world * bmax, p), dtype=base.dtype, device=base.device)
+        dist.all_gather_into_tensor(out, base, group=group)
+        return _rebuild(coeffs, lambda t: out.as_strided((world * bmax,) + tuple(t.shape[1:]),
+                                                        (p,) + tuple(t.stride()[1:]), t.storage_offset()))
     flat, meta = pack_coeffs(coeffs)
     if flat.shape[0] < bmax:
         pad = torch.zeros((bmax - flat.shape[0], flat.shape[1]), dtype=flat.dtype, device=flat.device)
         flat = torch.cat([flat, pad], 0)
     out = torch.empty((world * bmax, flat.shape[1]), dtype=flat.dtype, device=flat.device)
     dist.all_gather_into_tensor(out, flat, group=group)
-    if any(hi - lo != bmax for lo, hi in bounds):
+    if not even:
         out = torch.cat([out[r * bmax: r * bmax + (hi - lo)] for r, (lo, hi) in enumerate(bounds)], 0)
     return unpack_coeffs(out, meta)
+
+
+def transform_and_gather(transform, x_local: torch.Tensor, chunks: int = 4, group=None) -> list:
+    """Transform this rank's shard chunk by chunk and collect every chunk from all ranks, the collective of chunk k
+    overlapping the transform of chunk k + 1 (over NVLink the gather costs far more than the
+    transform, so it is the part to hide).  ``transform`` maps ``[b, ...]`` to a coefficient pytree (e.g.
+    ``lambda t: wavedec2(t, "db8", level=5)``).  Returns one gathered pytree per chunk; chunk ``k`` holds, for every
+    rank ``r`` in order, the items ``shard_bounds(B_local, chunks)[k]`` of that rank's shard (the ranks' shards must
+    have equal sizes)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    on_gpu = x_local.is_cuda
+    results = []
+    if on_gpu:
+        dev = x_local.device
+        cur = torch.cuda.current_stream(dev)
+        comm = _comm_stream(dev)
+        comm.wait_stream(cur)
+    for lo, hi in shard_bounds(x_local.shape[0], max(1, min(chunks, x_local.shape[0]))):
+        if hi == lo:
+            continue
+        c = transform(x_local[lo:hi])
+        if not on_gpu:
+            results.append(all_gather_coeffs(c, (hi - lo) * world, group))
+            continue
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(comm):
+            comm.wait_event(done)
+            results.append(all_gather_coeffs(c, (hi - lo) * world, group))
+            for t in _flatten(c)[0]:
+                t.record_stream(comm)
+    if on_gpu:
+        cur.wait_stream(comm)
+    return results
+
+
+_comm_streams: dict = {}
+
+
+def _comm_stream(dev: torch.device):
+    if dev not in _comm_streams:
+        _comm_streams[dev] = torch.cuda.Stream(device=dev)
+    return _comm_streams[dev]

@@ -78,3 +78,52 @@ def test_two_rank_gloo_gather_equals_unsharded_transform(total):
     res = sorted(q.get(timeout=10) for _ in range(2))
     assert all(ok for _, ok, _ in res), res
     assert res[0][2][0][0] == total
+
+
+def _packed_like_the_cuda_path(c):
+    """Coefficient pytree whose tensors are views of ONE [B, P] buffer -- the layout fwt._analysis returns."""
+    flat, meta = S.pack_coeffs(c)
+    views = S.unpack_coeffs(flat, meta)
+    assert S._packed_base(S._flatten(views)[0]) is not None
+    return views
+
+
+def _worker_packed(rank: int, world: int, port: int, total: int, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(9)
+        x = torch.randn(total, 20, 24, generator=g, dtype=torch.float64)
+        local = S.shard(x, rank, world)
+        want = P.wavedec2(x, "db2", level=2)
+        # (1) zero-copy path: the packed buffer itself is the message, the result is views of the gathered buffer
+        full = S.all_gather_coeffs(_packed_like_the_cuda_path(P.wavedec2(local, "db2", level=2)), total)
+        ok1 = type(full) is type(want) and all(torch.equal(a, b) for a, b in zip(flatten_coeffs(full), flatten_coeffs(want)))
+        ok1 = ok1 and S._packed_base(S._flatten(full)[0]) is not None
+        # (2) chunked transform + gather: chunk k holds rank-major the k-th slice of every shard
+        chunks = 2
+        res = S.transform_and_gather(lambda t: _packed_like_the_cuda_path(P.wavedec2(t, "db2", level=2)), local, chunks=chunks)
+        ok2 = len(res) == chunks
+        per = total // world
+        for k, (lo, hi) in enumerate(S.shard_bounds(per, chunks)):
+            idx = [r * per + i for r in range(world) for i in range(lo, hi)]
+            for a, b in zip(flatten_coeffs(res[k]), flatten_coeffs(want)):
+                ok2 = ok2 and torch.equal(a, b[idx])
+        q.put((rank, ok1, ok2))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_zero_copy_gather_and_chunked_overlap():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_packed, args=(r, 2, port, 8, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=10) for _ in range(2))
+    assert all(a and b for _, a, b in res), res
