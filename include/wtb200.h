@@ -221,6 +221,17 @@ int wt_matrix_axis_inv(int dtype, int filt_len, const double* rec_lo, const doub
                        int64_t x_outer_stride, int64_t x_axis_stride,
                        void* y, int64_t y_outer_stride, int64_t y_axis_stride, void* stream);
 
+/* Gradient of one transform level with respect to the filter taps along the contiguous axis (learnable wavelets:
+ * the reference's filters are nn.Parameters, src/ptwt/wavelets_learnable.py:167-189, and enter its convolutions through
+ * src/ptwt/_util.py:129-141).  out[k * L + t] = sum_{r, i} coeff_k[r, i] * sig[r, 2 i + t + 2 - L]  (k = 0 lo, 1 hi;
+ * samples outside [0, n) count as zero), accumulated in float64 into the DEVICE array out[2 * L] (zeroed here).
+ *   analysis level (zero extension of the explicitly extended input x):  coeff = upstream gradient of the band,
+ *       sig = x;   d dec_k[m] = out[k][L - 1 - m]
+ *   synthesis level: coeff = the band, sig = upstream gradient of the cropped output;  d rec_k[t] = out[k][t]
+ * rows of coeff_* are coeff_stride elements apart (m coefficients each), rows of sig sig_stride apart (n samples). */
+int wt_tap_corr(int dtype, int filt_len, const void* coeff_lo, const void* coeff_hi, int64_t coeff_stride,
+                const void* sig, int64_t sig_stride, int64_t rows, int64_t m, int64_t n, double* out, void* stream);
+
 /* Counters for bench.py's gpu_launches claim: kernels launched by this library on this
  * process since the last reset. */
 uint64_t wt_launch_count(void);

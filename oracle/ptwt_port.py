@@ -53,7 +53,8 @@ def _taps(wavelet: Any, dtype: torch.dtype, flip: bool):
     bank = filter_bank(as_wavelet(wavelet))
     out = []
     for f in bank:
-        t = (f.detach().cpu() if isinstance(f, torch.Tensor) else torch.tensor(list(map(float, f)), dtype=torch.float64)).to(dtype)
+        # tensors keep their autograd graph (the reference differentiates through learnable filters, _util.py:129-141)
+        t = (f.cpu() if isinstance(f, torch.Tensor) else torch.tensor(list(map(float, f)), dtype=torch.float64)).to(dtype)
         out.append(t.flip(-1) if flip else t)
     return out  # dec_lo, dec_hi, rec_lo, rec_hi
 

@@ -64,6 +64,7 @@ SIGNATURES = {
                                      C.c_int, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
     "wt_matrix_axis_inv": (C.c_int, [C.c_int, C.c_int, _f64p, _f64p, _i64, _i64, C.c_int, C.c_int, C.c_int, C.c_int,
                                      _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i64, _vp]),
+    "wt_tap_corr": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "wt_launch_count": (C.c_uint64, []),
     "wt_launch_count_reset": (None, []),
     "wt_set_knob": (C.c_int, [C.c_char_p, C.c_longlong]),

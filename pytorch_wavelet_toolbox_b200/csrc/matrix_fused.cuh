@@ -20,7 +20,7 @@
 
 namespace wtb {
 
-constexpr int MATF_MAXK = 6;
+constexpr int MATF_MAXK = 8;
 
 template <typename T>
 struct MatFusedParams {
@@ -37,7 +37,8 @@ struct MatFusedParams {
     const T* lo_right[MATF_MAXK];
     const T* hi_left[MATF_MAXK];
     const T* hi_right[MATF_MAXK];
-    int tk;                      // outputs of the last fused level per CTA
+    int tk;                      // outputs of the last fused level per chunk
+    int cpc;                     // consecutive chunks of one row a CTA streams through
     int cap0;                    // capacity (samples) of the level-0 staging arrays
     T flo[16], fhi[16];          // taps in window order: out[i] = sum_k f[k] a[2i - (L/2-1) + k]
 };
@@ -46,8 +47,8 @@ template <typename T> struct Vec2Of;
 template <> struct Vec2Of<double> { using type = double2; };
 template <> struct Vec2Of<float> { using type = float2; };
 
-template <typename T, int L>
-__global__ void __launch_bounds__(256) mat_fwd_fused_kernel(const __grid_constant__ MatFusedParams<T> p) {
+template <typename T, int L, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) mat_fwd_fused_kernel(const __grid_constant__ MatFusedParams<T> p) {
     using V2 = typename Vec2Of<T>::type;
     constexpr int HL = L / 2 - 1, HR = L / 2;
     constexpr int DELTA = HL & 1;                 // parity of the first sample of an even output's window
@@ -59,50 +60,82 @@ __global__ void __launch_bounds__(256) mat_fwd_fused_kernel(const __grid_constan
     T* bufA = reinterpret_cast<T*>(smem_raw);     // even | odd arrays of the current level input
     const int capA = p.cap0 / 2 + 8;              // entries per polyphase array (level 0)
     T* bufB = bufA + 2 * capA;                    // even | odd arrays of the next level
+    // interleaved samples of the NEXT chunk, filled by cp.async (16-byte aligned destination)
+    T* raw = reinterpret_cast<T*>((reinterpret_cast<uintptr_t>(bufB + 2 * (p.cap0 / 4 + 16)) + 15) & ~uintptr_t(15));
 
     const int tid = threadIdx.x;
     const int b = blockIdx.y;
     const int K = p.k;
+    const T* __restrict__ xb = p.x + (int64_t)b * p.x_stride;
 
-    // ranges: rlo[j], rhi[j] = level-j indices this CTA computes (j >= 1) / stages (j = 0)
-    int rlo[MATF_MAXK + 1], rhi[MATF_MAXK + 1];
-    rlo[K] = blockIdx.x * p.tk;
-    rhi[K] = min(rlo[K] + p.tk, p.n[K]);
-    if (rlo[K] >= p.n[K]) return;
-#pragma unroll
-    for (int j = MATF_MAXK; j >= 1; --j) {
-        if (j > K) continue;
-        const int half = p.n[j];                  // outputs of level j
-        int lo = 2 * rlo[j] - HL, hi = 2 * (rhi[j] - 1) + HR + 1;
-        if (rlo[j] < p.nb_top[j - 1]) lo = 0, hi = max(hi, p.w_left[j - 1]);
-        if (rhi[j] > half - p.nb_bot[j - 1]) hi = p.n[j - 1], lo = min(lo, p.n[j - 1] - p.w_right[j - 1]);
-        lo = max(lo, 0) & ~3;                     // multiple of 4: polyphase index starts even
-        hi = min(hi, p.n[j - 1]);
-        rlo[j - 1] = lo;
-        rhi[j - 1] = hi;
-        if (j - 1 >= 1) {
-            // the computed range of level j-1 must start on an even output and stay inside its own extent
-            rlo[j - 1] = lo;
+    // A CTA streams `cpc` consecutive chunks of one row: while chunk c is taken through the K levels, the samples of
+    // chunk c + 1 travel into `raw` with cp.async (round 1 staged, synchronised and only then computed: 28 %).
+    // ranges: rlo[j], rhi[j] = level-j indices this CTA computes (j >= 1) / stages (j = 0) for one chunk; two sets in
+    // shared memory (current chunk / prefetched chunk).  In registers the run-time level index costs a local array.
+    __shared__ int s_r[2][2][MATF_MAXK + 1];
+    const int nchunks = (p.n[K] + p.tk - 1) / p.tk;
+    const int c_first = blockIdx.x * p.cpc, c_last = min(c_first + p.cpc, nchunks);
+    if (c_first >= nchunks) return;
+    auto ranges = [&](int chunk, int set) {
+        int lo_j = chunk * p.tk, hi_j = min(lo_j + p.tk, p.n[K]);
+        s_r[set][0][K] = lo_j; s_r[set][1][K] = hi_j;
+        for (int j = K; j >= 1; --j) {
+            const int half = p.n[j];                  // outputs of level j
+            int lo = 2 * lo_j - HL, hi = 2 * (hi_j - 1) + HR + 1;
+            if (lo_j < p.nb_top[j - 1]) lo = 0, hi = max(hi, p.w_left[j - 1]);
+            if (hi_j > half - p.nb_bot[j - 1]) hi = p.n[j - 1], lo = min(lo, p.n[j - 1] - p.w_right[j - 1]);
+            lo = max(lo, 0) & ~3;                     // multiple of 4: polyphase index starts even
+            hi = min(hi, p.n[j - 1]);
+            s_r[set][0][j - 1] = lo_j = lo;
+            s_r[set][1][j - 1] = hi_j = hi;
         }
-    }
+    };
+    // asynchronous copy of samples [s0, s1) of the row into raw[0 ..): 16-byte pieces, element-sized tail
+    auto prefetch = [&](int s0, int s1) {
+        constexpr int VE = 16 / (int)sizeof(T);
+        const int cnt = s1 - s0;
+        const int nv = ((uintptr_t)(xb + s0) & 15) ? 0 : cnt / VE;   // float rows with a stride of 2 (mod 4) samples
+        for (int q = tid; q < nv; q += NT) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(raw + VE * q);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(xb + s0 + VE * q) : "memory");
+        }
+        for (int q = nv * VE + tid; q < cnt; q += NT) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(raw + q);
+            if (sizeof(T) == 8)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(xb + s0 + q) : "memory");
+            else
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(xb + s0 + q) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (tid == 0) ranges(c_first, 0);
+    __syncthreads();
+    prefetch(s_r[0][0][0], s_r[0][1][0]);
 
-    // stage the level-0 samples, de-interleaved
+    int set = 0;
+    for (int chunk = c_first; chunk < c_last; ++chunk, set ^= 1) {
+    const int* rlo = s_r[set][0];
+    const int* rhi = s_r[set][1];
+    if (tid == 0 && chunk + 1 < c_last) ranges(chunk + 1, set ^ 1);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                                  // raw holds this chunk; the next chunk's ranges are visible
+
+    // de-interleave the staged samples: raw -> even | odd polyphase arrays
     {
-        const T* __restrict__ xb = p.x + (int64_t)b * p.x_stride;
-        const int s0 = rlo[0], cnt = rhi[0] - rlo[0];
+        const int cnt = rhi[0] - rlo[0];
         T* ev = bufA;
         T* od = bufA + capA;
-        for (int q = tid; 2 * q < cnt; q += 256) {
-            const int s = s0 + 2 * q;
-            if (s + 1 < rhi[0]) {
-                const V2 v = __ldg(reinterpret_cast<const V2*>(xb + s));   // s is even and the row start is aligned
+        for (int q = tid; 2 * q < cnt; q += NT) {
+            if (2 * q + 1 < cnt) {
+                const V2 v = *reinterpret_cast<const V2*>(raw + 2 * q);
                 ev[q] = v.x; od[q] = v.y;
             } else {
-                ev[q] = __ldg(xb + s); od[q] = T(0);
+                ev[q] = raw[2 * q]; od[q] = T(0);
             }
         }
     }
-    __syncthreads();
+    __syncthreads();                                  // raw is free again
+    if (chunk + 1 < c_last) prefetch(s_r[set ^ 1][0][0], s_r[set ^ 1][1][0]);
 
     T* cur = bufA;
     int cur_cap = capA;
@@ -117,12 +150,14 @@ __global__ void __launch_bounds__(256) mat_fwd_fused_kernel(const __grid_constan
         const T* od = cur + cur_cap;
         T* nev = nxt;
         T* nod = nxt + nxt_cap;
-        const int own0 = (blockIdx.x * p.tk) << (K - j), own1 = min(((blockIdx.x + 1) * p.tk) << (K - j), half);
+        const int own0 = (chunk * p.tk) << (K - j), own1 = min(((chunk + 1) * p.tk) << (K - j), half);
         T* __restrict__ hib = p.hi[j - 1] + (int64_t)b * p.hi_stride[j - 1];
         T* __restrict__ lob = p.lo + (int64_t)b * p.lo_stride;
         const int nbt = p.nb_top[j - 1], nbb = p.nb_bot[j - 1];
         const int npairs = (rhi[j] - rlo[j] + 1) / 2;
-        for (int pr = tid; pr < npairs; pr += 256) {
+        const bool vec_ok = !((uintptr_t)hib & (2 * sizeof(T) - 1)) && !(p.hi_stride[j - 1] & 1) &&
+                            (j < K || (!((uintptr_t)lob & (2 * sizeof(T) - 1)) && !(p.lo_stride & 1)));
+        for (int pr = tid; pr < npairs; pr += NT) {
             const int i = rlo[j] + 2 * pr;        // even output index
             T alo[2] = {T(0), T(0)}, ahi[2] = {T(0), T(0)};
             const int q0 = ((2 * i - HL - in0) >> 1) - PQ;           // even polyphase index of the first load
@@ -147,6 +182,7 @@ __global__ void __launch_bounds__(256) mat_fwd_fused_kernel(const __grid_constan
                     }
                 }
             } else {
+#pragma unroll
                 for (int r = 0; r < 2; ++r) {
                     const int ii = i + r;
                     if (ii >= half) continue;
@@ -195,12 +231,19 @@ __global__ void __launch_bounds__(256) mat_fwd_fused_kernel(const __grid_constan
             // approximation -> next level (de-interleaved), detail -> HBM (owned range only)
             const int rel = (i - rlo[j]) >> 1;
             if (j < K) { nev[rel] = alo[0]; nod[rel] = alo[1]; }
+            if (i >= own0 && i + 1 < own1 && vec_ok) {
+                // i is even and the rows are 16-byte aligned: one 128-bit (f64) / 64-bit (f32) store per band
+                V2 hv; hv.x = ahi[0]; hv.y = ahi[1];
+                *reinterpret_cast<V2*>(hib + i) = hv;
+                if (j == K) { V2 lv; lv.x = alo[0]; lv.y = alo[1]; *reinterpret_cast<V2*>(lob + i) = lv; }
+            } else {
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int ii = i + r;
-                if (ii >= own0 && ii < own1) {
-                    hib[ii] = ahi[r];
-                    if (j == K) lob[ii] = alo[r];
+                for (int r = 0; r < 2; ++r) {
+                    const int ii = i + r;
+                    if (ii >= own0 && ii < own1) {
+                        hib[ii] = ahi[r];
+                        if (j == K) lob[ii] = alo[r];
+                    }
                 }
             }
         }
@@ -208,6 +251,7 @@ __global__ void __launch_bounds__(256) mat_fwd_fused_kernel(const __grid_constan
         T* t = const_cast<T*>(cur); cur = nxt; nxt = t;
         cur_cap = nxt_cap;
     }
+    }   // chunks of this CTA
 }
 
 
@@ -237,8 +281,9 @@ static bool launch_mat_fwd_fused(int L, int k, const int64_t* n, const int32_t* 
     p.lo = lo_out; p.lo_stride = lo_stride;
     for (int q = 0; q < L; ++q) { p.flo[q] = taps.lo[L - 1 - q]; p.fhi[q] = taps.hi[L - 1 - q]; }
     const int nk = p.n[k];
-    int chunk0 = sizeof(T) == 8 ? 8192 : 16384;                   // level-0 samples per CTA (tools/ab_matrix.py)
+    int chunk0 = sizeof(T) == 8 ? 2048 : 4096;                    // level-0 samples per chunk (tools/ab_matrix2.py)
     if (knob_is_set(K_MATF_CHUNK)) { const int v = (int)knob_val(K_MATF_CHUNK, 0); if (v >= 64 && v <= 16384) chunk0 = v; }
+    if (n[0] <= 8192 && n[0] > chunk0) chunk0 = (int)n[0];        // short rows: the whole row is one chunk
     int tk = chunk0 >> k;
     if (tk < 4) tk = 4;
     tk = (tk + 3) & ~3;
@@ -248,20 +293,36 @@ static bool launch_mat_fwd_fused(int L, int k, const int64_t* n, const int32_t* 
     if (cap0 > p.n[0] + 16) cap0 = (p.n[0] + 16 + 3) & ~3;
     cap0 = (cap0 + 3) & ~3;
     p.cap0 = cap0;
-    const size_t smem = (size_t)(2 * (cap0 / 2 + 8) + 2 * (cap0 / 4 + 16)) * sizeof(T);
+    const size_t smem = (size_t)(2 * (cap0 / 2 + 8) + 2 * (cap0 / 4 + 16) + cap0) * sizeof(T) + 16;
     if (smem > 200 * 1024) return false;
-    dim3 grid((nk + tk - 1) / tk, (unsigned)batch);
+    const int nchunks = (nk + tk - 1) / tk;
+    int cpc = (int)knob_val(K_MATF_CPC, 8);
+    if (cpc < 1) cpc = 1;
+    while (cpc > 1 && (int64_t)((nchunks + cpc - 1) / cpc) * batch < 4 * 148) cpc /= 2;   // keep the machine full
+    p.cpc = cpc;
+    dim3 grid((nchunks + cpc - 1) / cpc, (unsigned)batch);
+    // CTA shape: 128 threads for small chunks (more CTAs per SM: the staging loads of one overlap the cascade of the
+    // others), 256 for large ones.  MATF_NT / MATF_MINB override (tools/ab_matrix.py).
+    int nt = chunk0 <= 2048 ? 128 : 256;
+    if (knob_is_set(K_MATF_NT)) nt = knob_val(K_MATF_NT, 256) == 128 ? 128 : 256;
+    const int minb = (int)knob_val(K_MATF_MINB, 1);
+#define WTB_MF_LAUNCH(LL, NTT, MB)                                                                              \
+    {                                                                                                           \
+        cudaError_t e = ensure_dyn_smem(mat_fwd_fused_kernel<T, LL, NTT, MB>, smem > 200 * 1024 ? smem : 200 * 1024); \
+        if (e != cudaSuccess) { *err = e; return true; }                                                        \
+        mat_fwd_fused_kernel<T, LL, NTT, MB><<<grid, NTT, smem, st>>>(p);                                       \
+    }
 #define WTB_MF(LL)                                                                                              \
     case LL: {                                                                                                  \
-        cudaError_t e = ensure_dyn_smem(mat_fwd_fused_kernel<T, LL>, smem > 200 * 1024 ? smem : 200 * 1024);         \
-        if (e != cudaSuccess) { *err = e; return true; }                                                        \
-        mat_fwd_fused_kernel<T, LL><<<grid, 256, smem, st>>>(p);                                                \
+        if (nt == 128) { if (minb > 1) WTB_MF_LAUNCH(LL, 128, 6) else WTB_MF_LAUNCH(LL, 128, 1) }                  \
+        else { if (minb > 1) WTB_MF_LAUNCH(LL, 256, 3) else WTB_MF_LAUNCH(LL, 256, 1) }                            \
         break;                                                                                                  \
     }
     switch (L) {
         WTB_MF(2) WTB_MF(4) WTB_MF(6) WTB_MF(8) WTB_MF(10) WTB_MF(12) WTB_MF(14) WTB_MF(16)
         default: return false;
     }
+#undef WTB_MF_LAUNCH
 #undef WTB_MF
     *err = cudaGetLastError();
     return true;

@@ -18,6 +18,7 @@
 #include "axis1d_fast.cuh"
 #include "matrix_fused.cuh"
 #include "axis1d_fused.cuh"
+#include "tap_grad.cuh"
 #if !defined(WTB_NO_FUSED) && !__has_include("fused2d.cuh")
 #define WTB_NO_FUSED 1
 #endif
@@ -554,7 +555,9 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
         if (allow_fused && !knob_on(K_DISABLE_FUSED)) {
             // group of consecutive unpadded levels -> one fused launch
             int k = 0;
-            int kmax = 4;  // measured on config 4 (tools/ab_matrix.py): 4 levels x 4096-sample chunks beat 6 x 4096
+            // 4 levels per launch while a row is cut into chunks (halo grows with 2^k), all remaining levels (up to
+            // MATF_MAXK) once a whole row fits one chunk -- tools/ab_matrix2.py
+            int kmax = n[l] <= 8192 ? MATF_MAXK : 4;
             if (knob_is_set(K_MATF_K)) { const int v = (int)knob_val(K_MATF_K, 0); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
             while (l + k < levels && k < kmax && !padded[l + k] && !(n[l + k] & 1) &&
                    (k == 0 || n[l + k] == n[l + k - 1] / 2))
@@ -957,6 +960,24 @@ int wt_matrix_axis_inv(int dtype, int filt_len, const double* rec_lo, const doub
                                     x, outer, inner, x_outer_stride, x_axis_stride, y, y_outer_stride, y_axis_stride, st);
     return matrix_axis_t<double>(true, filt_len, rec_lo, rec_hi, n, n, keep, WT_MODE_ZERO, nb_top, nb_bot, w_left, w_right, blocks,
                                  x, outer, inner, x_outer_stride, x_axis_stride, y, y_outer_stride, y_axis_stride, st);
+}
+
+int wt_tap_corr(int dtype, int filt_len, const void* coeff_lo, const void* coeff_hi, int64_t coeff_stride,
+                const void* sig, int64_t sig_stride, int64_t rows, int64_t m, int64_t n, double* out, void* stream) {
+    if (dtype != WT_F32 && dtype != WT_F64) return fail(WT_EINVAL, "dtype must be WT_F32 or WT_F64");
+    if (filt_len < 2 || filt_len > WT_MAX_FILT_LEN) return fail(WT_EUNSUPPORTED, "filter length %d", filt_len);
+    if (!out || rows < 0 || m < 0 || n < 0 || m >= (int64_t(1) << 30) || n >= (int64_t(1) << 31) - 2 * WT_MAX_FILT_LEN)
+        return fail(WT_EINVAL, "bad argument");
+    if (rows > 0 && m > 0 && (!coeff_lo || !coeff_hi || !sig)) return fail(WT_EINVAL, "NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = dtype == WT_F32
+        ? launch_tap_corr<float>((const float*)coeff_lo, (const float*)coeff_hi, coeff_stride, (const float*)sig, sig_stride,
+                                 rows, (int)m, (int)n, filt_len, out, st)
+        : launch_tap_corr<double>((const double*)coeff_lo, (const double*)coeff_hi, coeff_stride, (const double*)sig,
+                                  sig_stride, rows, (int)m, (int)n, filt_len, out, st);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) return cuda_fail(e, "tap_corr_kernel");
+    return 0;
 }
 
 uint64_t wt_launch_count(void) { return g_launches.load(); }

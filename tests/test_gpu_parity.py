@@ -384,23 +384,69 @@ def test_autograd_matches_the_reference_operators(mode):
             assert_close_rel(a.grad, b.grad, scale=10.0, what=f"grad of {inv.__name__}")
 
 
-def test_autograd_cpu_leaf_and_filter_grads_rejected():
+def test_autograd_cpu_leaf_and_matrix_grads_rejected():
     x = torch.randn(2, 64, requires_grad=True)
     c = wt.wavedec(x, "db2", level=2)            # CPU leaf: staged to the GPU, gradients come back on the CPU
     sum(t.sum() for t in c).backward()
     xr = x.detach().clone().requires_grad_(True)
     sum(t.sum() for t in P.wavedec(xr, "db2", level=2)).backward()
     assert x.grad.device.type == "cpu" and torch.allclose(x.grad, xr.grad, atol=1e-5)
-    from pytorch_wavelet_toolbox_b200._wavelets import as_wavelet
-
-    tt = wt.WaveletTensorTuple.from_wavelet(as_wavelet("db2"), torch.float32)
-    learn = wt.WaveletTensorTuple(*[t.clone().requires_grad_(True) for t in tt])
-    with pytest.raises(NotImplementedError):
-        wt.wavedec(torch.randn(2, 64, device=DEV), learn, level=1)
-    with torch.no_grad():
-        wt.wavedec(torch.randn(2, 64, device=DEV), learn, level=1)
     with pytest.raises(NotImplementedError):
         wt.MatrixWavedec("haar", 2)(torch.randn(2, 32, device=DEV, requires_grad=True))
+
+
+def _learnable(name, dtype=torch.float64, device="cpu"):
+    from pytorch_wavelet_toolbox_b200._wavelets import as_wavelet
+
+    tt = wt.WaveletTensorTuple.from_wavelet(as_wavelet(name), dtype)
+    return wt.WaveletTensorTuple(*[t.clone().to(device).requires_grad_(True) for t in tt])
+
+
+@pytest.mark.parametrize("mode", ["zero", "reflect", "constant", "periodic", "symmetric"])
+def test_filter_tap_gradients_match_the_reference_operators(mode):
+    """SURVEY 8f row 3, second half: learnable wavelets.  Gradients w.r.t. the four filters (and the data) through
+    wavedec* / waverec* equal those of the reference's torch-operator chain (the oracle port under autograd, float64;
+    the reference builds its conv kernels from the filter tensors, _util.py:129-141)."""
+    g = torch.Generator().manual_seed(41)
+    cases = [
+        (wt.wavedec, P.wavedec, wt.waverec, P.waverec, torch.randn(3, 41, generator=g, dtype=torch.float64), "db3", 2),
+        (wt.wavedec2, P.wavedec2, wt.waverec2, P.waverec2, torch.randn(2, 30, 37, generator=g, dtype=torch.float64), "db2", 2),
+        (wt.wavedec3, P.wavedec3, wt.waverec3, P.waverec3, torch.randn(2, 12, 15, 14, generator=g, dtype=torch.float64), "db2", 1),
+    ]
+    for fwd, pfwd, inv, pinv, x, wav, level in cases:
+        wa, wb = _learnable(wav), _learnable(wav)
+        xa = x.clone().requires_grad_(True)
+        xb = x.clone().requires_grad_(True)
+        ca = fwd(xa.to(DEV), wa, mode=mode, level=level)
+        cb = pfwd(xb, wb, mode=mode, level=level)
+        for a, b in zip(flatten_coeffs(ca), flatten_coeffs(cb)):
+            assert_close_rel(a, b, scale=float(b.abs().max()) + 1.0, what=f"forward with learnable filters {mode}")
+        ya = inv(ca, wa)
+        yb = pinv(cb, wb)
+        w = torch.randn(yb.shape, generator=g, dtype=torch.float64)
+        (_weighted_sum(ca, 7) + (ya * w.to(DEV)).sum()).backward()
+        (_weighted_sum(cb, 7) + (yb * w).sum()).backward()
+        assert_close_rel(xa.grad, xb.grad, scale=float(xb.grad.abs().max()), what=f"data grad {fwd.__name__} {mode}")
+        for name, ta, tb in zip(("dec_lo", "dec_hi", "rec_lo", "rec_hi"), wa, wb):
+            assert ta.grad is not None, f"{name} got no gradient ({fwd.__name__} {mode})"
+            scale = max(float(t.grad.abs().max()) for t in wb)
+            assert_close_rel(ta.grad, tb.grad, scale=scale, what=f"{name} grad of {fwd.__name__} {mode}")
+
+
+def test_filter_tap_gradients_first_layer_and_float32():
+    """Data without grad, filters with grad (the usual first-layer case): the filters still get their gradient; float32
+    filters on the GPU get float32 gradients on the GPU."""
+    g = torch.Generator().manual_seed(43)
+    x = torch.randn(4, 200, generator=g)
+    wa, wb = _learnable("db4", torch.float32, DEV), _learnable("db4", torch.float32)
+    ca = wt.wavedec(x.to(DEV), wa, level=3)
+    cb = P.wavedec(x, wb, level=3)
+    _weighted_sum(ca, 3).backward()
+    _weighted_sum(cb, 3).backward()
+    for ta, tb in zip(wa[:2], wb[:2]):
+        assert ta.grad.is_cuda and ta.grad.dtype == torch.float32
+        assert float((ta.grad.cpu() - tb.grad).abs().max()) <= 2e-4 * float(tb.grad.abs().max())
+    assert wa[2].grad is None and wa[3].grad is None   # the reconstruction filters were not used
 
 
 def test_host_pipeline_equals_device_path(monkeypatch):
