@@ -291,6 +291,11 @@ def host_link_probe(dev, seconds: float = 0.6) -> dict:
     return {"h2d_plus_d2h_gbs": 2 * n * reps / dt / 1e9, "seconds": dt}
 
 
+def _dbg(msg: str) -> None:
+    if os.environ.get("BENCH_DEBUG"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -329,7 +334,18 @@ def main() -> None:
         import torch.distributed as dist_mod
 
         dist = dist_mod
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL announces its version on stdout at the first collective: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if dist is not None:
@@ -343,6 +359,7 @@ def main() -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    _dbg("process group up")
     B = args.batch or cfg["shape"][0]
     shape = (B,) + tuple(cfg["shape"][1:])
     dtype = DT[cfg["dtype"]]
@@ -359,6 +376,7 @@ def main() -> None:
     del out
     torch.cuda.synchronize(dev)
 
+    _dbg("warm-up done")
     sampler = ClockSampler(local)
     _native.launch_count_reset()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -380,6 +398,7 @@ def main() -> None:
     ms_per_step = total_ms / args.steps
     value = world * n_samples / (ms_per_step * 1e-3) / 1e6
 
+    _dbg("timed region done")
     # parity of what was just timed against the oracle, outside the timed region: items from BOTH halves of the batch
     # (the second half runs on the library's auxiliary stream with reused scratch slots in the 2-D analysis)
     parity = None
@@ -401,6 +420,7 @@ def main() -> None:
                   "tolerance": 1e-5 if dtype == torch.float32 else 1e-11}
     del out
 
+    _dbg("parity done")
     # roofline of the dominant kernel: timed alone with CUDA events on the launching stream (a transform with
     # level = kernel_level is exactly that launch); achieved = its algorithmic bytes / its average duration
     peak, peak_src = measured_peak_gbs()
@@ -434,6 +454,7 @@ def main() -> None:
         except Exception:  # noqa: BLE001
             traffic = None
 
+    _dbg("kernel timing done")
     # inverse transform of the same coefficients (reported separately)
     coeffs = fwd(x)
     for _ in range(3):
@@ -452,6 +473,7 @@ def main() -> None:
                "step_frac": alg / (inv_ms * 1e-3) / 1e9 / peak, "round_trip_max_abs_err": rt_err}
     del rec
 
+    _dbg("inverse done")
     # the NCCL collection of the shards: ONE all_gather of the already packed coefficient buffer per chunk,
     # issued on a second stream so that chunk k travels while chunk k+1 is transformed
     gather = None
@@ -480,6 +502,7 @@ def main() -> None:
     else:
         del coeffs
 
+    _dbg("gather done")
     # end to end through the public API with HOST (pinned) buffers: H2D + transform + D2H every step
     e2e, link = None, None
     if not args.no_e2e:
@@ -502,6 +525,7 @@ def main() -> None:
                "staging": "pinned host output buffer reused across steps (wt.host_staging(reuse=True))"}
         del oh, xh
 
+    _dbg("e2e done")
     # the incumbent on this GPU: the reference's own algorithm executed by torch/cuDNN on the same device -- what ptwt
     # does today when it is handed CUDA tensors.  Informational: a sample of the batch, device-resident, CUDA events.
     incumbent = None
@@ -535,6 +559,7 @@ def main() -> None:
     if rank == 0 and not args.no_cpu:
         cpu, _, _, _ = cpu_reference(cfg, args.cpu_batch or cfg["cpu_batch"], 3)
 
+    _dbg("assembling the line")
     if rank == 0:
         in_mb, out_mb = nbytes([x]) / 1e6, d2h_bytes / 1e6
         line = {

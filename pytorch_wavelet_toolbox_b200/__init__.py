@@ -25,6 +25,7 @@ from .fwt import host_staging, wavedec, wavedec2, wavedec3, waverec, waverec2, w
 from .matrix_fwt import MatrixWavedec, MatrixWaverec, construct_boundary_a, construct_boundary_s
 from .matrix_fwt_nd import MatrixWavedec2, MatrixWavedec3, MatrixWaverec2, MatrixWaverec3
 from .separable import fswavedec2, fswavedec3, fswaverec2, fswaverec3
+from .packets import WaveletPacket, WaveletPacket2D
 
 __version__ = "0.1.0"
 
@@ -35,6 +36,7 @@ HOT_PATH_NAMES = (
 NEXT_ROW_NAMES = (
     "fswavedec2", "fswavedec3", "fswaverec2", "fswaverec3",
     "MatrixWavedec2", "MatrixWaverec2", "MatrixWavedec3", "MatrixWaverec3",  # separable mode only
+    "WaveletPacket", "WaveletPacket2D",                                      # level-wise batched node expansion
 )
 
 __all__ = list(HOT_PATH_NAMES) + list(NEXT_ROW_NAMES) + [
@@ -55,7 +57,22 @@ def install() -> list[str]:
     """
     import importlib
     import sys
+    import warnings
 
+    import torch
+
+    from . import _native
+
+    # This backend has no CPU compute path: on a machine without a usable CUDA device (or without the built library)
+    # rebinding would turn a working CPU ptwt into a failing one, so nothing is touched there.
+    try:
+        usable = torch.cuda.is_available() and _native.load() is not None
+    except Exception:  # noqa: BLE001
+        usable = False
+    if not usable:
+        warnings.warn("pytorch_wavelet_toolbox_b200.install(): no CUDA device / libwtb200.so -- ptwt left untouched",
+                      RuntimeWarning, stacklevel=2)
+        return []
     ptwt = importlib.import_module("ptwt")
     mine = {name: globals()[name] for name in HOT_PATH_NAMES + NEXT_ROW_NAMES}
     replaced = []

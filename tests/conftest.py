@@ -67,7 +67,9 @@ def flatten_coeffs(coeffs):
     return out
 
 
-#: stated tolerances of the parity gate: |delta| <= TOL[dtype] * max|coefficient|
+#: stated tolerances of the parity gate: |delta| <= TOL[dtype] * max|coefficient| -- the scale
+#: is always max|reference value| of the compared tensor (or of the coefficient tree it belongs to), never a looser
+#: constant (round 1 used 10.0 / 10 * max|x| in places)
 TOL = {torch.float32: 1e-5, torch.float64: 1e-11}
 
 

@@ -248,3 +248,45 @@ def test_separable_matrix_level_walk_matches_the_reference_warning(capsys):
     ours2 = capsys.readouterr().err
     ptwt.MatrixWavedec2("db3", 3)(torch.randn(20, 12, dtype=torch.float64))
     assert capsys.readouterr().err == ours2
+
+
+def test_signatures_equal_the_reference_functions():
+    """Every public callable has the parameter names, kinds and defaults of the reference function of the same name
+    (checked against the unmodified reference itself whenever it is importable here)."""
+    import inspect
+
+    from oracle.ref_import import import_reference, reference_available
+    if not reference_available():
+        pytest.skip("/root/reference is not present on this machine")
+    ptwt = import_reference()
+
+    def params(fn):
+        return [(n, p.kind, p.default) for n, p in inspect.signature(fn).parameters.items() if n != "self"]
+
+    for name in ("wavedec", "waverec", "wavedec2", "waverec2", "wavedec3", "waverec3", "fswavedec2", "fswavedec3",
+                 "fswaverec2", "fswaverec3"):
+        assert params(getattr(wt, name)) == params(getattr(ptwt, name)), name
+    for name in ("MatrixWavedec", "MatrixWaverec", "MatrixWavedec2", "MatrixWaverec2", "MatrixWavedec3", "MatrixWaverec3"):
+        ours = [q for q in params(getattr(wt, name).__init__) if q[1] is not inspect.Parameter.VAR_KEYWORD]
+        ref = [q for q in params(inspect.unwrap(getattr(ptwt, name).__init__)) if q[1] is not inspect.Parameter.VAR_KEYWORD]
+        assert ours == ref, name
+    for name in ("WaveletPacket", "WaveletPacket2D"):
+        ours = [q[0] for q in params(getattr(wt, name).__init__) if q[1] is not inspect.Parameter.VAR_KEYWORD]
+        ref = [q[0] for q in params(inspect.unwrap(getattr(ptwt, name).__init__))]
+        assert ours == ref, name
+
+
+def test_install_leaves_a_cpu_only_machine_alone():
+    """Without a CUDA device install() must not turn a working CPU ptwt into a failing one."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from oracle.ref_import import import_reference, reference_available
+    if not reference_available():
+        pytest.skip("/root/reference is not present on this machine")
+    ptwt = import_reference()
+    before = ptwt.wavedec
+    with pytest.warns(RuntimeWarning):
+        assert wt.install() == []
+    assert ptwt.wavedec is before and ptwt.packets.wavedec is before
+    c = ptwt.wavedec(torch.arange(16.0), "haar", mode="zero", level=2)
+    assert [t.shape[-1] for t in c] == [4, 4, 8]
