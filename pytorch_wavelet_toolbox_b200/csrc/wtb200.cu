@@ -17,6 +17,7 @@
 #include "matrix_generic.cuh"
 #include "axis1d_fast.cuh"
 #include "matrix_fused.cuh"
+#include "matrix_dmma.cuh"
 #include "axis1d_fused.cuh"
 #include "tap_grad.cuh"
 #if !defined(WTB_NO_FUSED) && !__has_include("fused2d.cuh")
@@ -567,7 +568,16 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
                 T* lo_dst = last ? (T*)lo_out : ping[(l + k - 1) & 1];
                 const int64_t lo_ds = last ? lo_stride : n[l + k - 1] / 2;
                 cudaError_t e = cudaSuccess;
-                if (launch_mat_fwd_fused<T>(L, k, n + l, nbt + l, nbb + l, wt + l, wb + l, bptr + 4 * l, src, src_stride, batch,
+                bool launched = false;
+                if constexpr (sizeof(T) == 8) {
+                    // float64: the band contraction on the FP64 tensor cores (matrix_dmma.cuh)
+                    if (!knob_on(K_NO_DMMA))
+                        launched = launch_mat_fwd_dmma(L, k, n + l, nbt + l, nbb + l, wt + l, wb + l,
+                                                       (const double* const*)(bptr + 4 * l), (const double*)src, src_stride, batch,
+                                                       hi_out + l, hi_stride + l, (double*)lo_dst, lo_ds, taps, st, &e);
+                }
+                if (launched ||
+                    launch_mat_fwd_fused<T>(L, k, n + l, nbt + l, nbb + l, wt + l, wb + l, bptr + 4 * l, src, src_stride, batch,
                                             hi_out + l, hi_stride + l, lo_dst, lo_ds, taps, st, &e)) {
                     g_launches.fetch_add(1, std::memory_order_relaxed);
                     if (e != cudaSuccess) return cuda_fail(e, "mat_fwd_fused_kernel");
