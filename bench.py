@@ -93,21 +93,25 @@ def samples_of(shape) -> int:
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is started
+    before the warm-up (nvidia-smi needs a few hundred ms to come up, longer on an 8-GPU box) and the samples are cut to
+    the timed window by their timestamps; if the window is shorter than the sampling period the samples taken under the
+    identical warm-up load are used and the record says so."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
         self.proc = None
-        self.lines: list[str] = []
+        self.lines: list[tuple[float, str]] = []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -116,7 +120,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def window_begin(self):
+        self.t0 = time.time()
+
+    def window_end(self):
+        self.t1 = time.time()
 
     def stop(self) -> dict:
         if self.proc is None:
@@ -127,22 +137,32 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [v.strip() for v in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
+
+        def parse(rows):
+            sm, mx, reasons = [], [], set()
+            for _, ln in rows:
+                f = [v.strip() for v in ln.split(",")]
+                if len(f) < 10:
+                    continue
+                try:
+                    sm.append(float(f[2]))
+                    mx.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[6:10]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            sm.sort()
+            return sm, mx, reasons
+
+        inside = [r for r in self.lines if self.t0 is not None and self.t0 - 0.01 <= r[0] <= (self.t1 or 1e30) + 0.03]
+        window = "timed region"
+        sm, mx, reasons = parse(inside)
+        if not sm:
+            window = "warm-up + timed region (the timed region is shorter than the sampling period)"
+            sm, mx, reasons = parse(self.lines)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def measured_peak_gbs() -> tuple[float, str]:
@@ -369,19 +389,24 @@ def main() -> None:
     fwd = make_forward(wt, cfg)
     inv = make_inverse(wt, cfg)
 
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_w = time.time()
     for _ in range(max(args.warmup, 3)):
         out = fwd(x)
     alg = nbytes([x]) + nbytes(flat(out))     # algorithmic bytes: input read once + every returned coefficient written once
     d2h_bytes = nbytes(flat(out))
-    del out
     torch.cuda.synchronize(dev)
+    while time.time() - t_w < 0.6:            # let nvidia-smi come up under the same load (not timed)
+        out = fwd(x)
+        torch.cuda.synchronize(dev)
+    del out
 
     _dbg("warm-up done")
-    sampler = ClockSampler(local)
     _native.launch_count_reset()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    sampler.start()
+    sampler.window_begin()
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record()
@@ -391,6 +416,7 @@ def main() -> None:
         ev[i][1].record()
     t_end.record()
     barrier()
+    sampler.window_end()
     clocks = sampler.stop()
     launches = _native.launch_count()
     total_ms = max_over_ranks(t_start.elapsed_time(t_end))
