@@ -39,7 +39,7 @@ CONFIGS = {
             kernel="fwd3d_tile_kernel<8> (level-1 launch)", kernel_level=1),
     4: dict(kind="matrix", wavelet="db6", level=None, mode="zero", shape=(1024, 65536), dtype="f64", cpu_batch=16,
             metric="Msamples/s, MatrixWavedec db6 65536 fp64 (forward)", baseline_cfg="BASELINE.json configs[3]",
-            kernel="mat_fwd_fused_kernel<double,12> (first group of 4 levels)", kernel_level=4),
+            kernel="mat_fwd_dmma_kernel<12,128> (FP64 tensor cores; first group of 4 levels)", kernel_level=4),
     5: dict(kind="2d", wavelet="db8", level=5, mode="reflect", shape=(512, 2048, 2048), dtype="f32", cpu_batch=8,
             metric="Msamples/s, wavedec2 db8 L5 2048x2048 fp32 (forward)", baseline_cfg="BASELINE.json configs[4]",
             kernel="fwd2d_strip_f32_kernel<16,64,TMA> (level-1 launch)", kernel_level=1),
@@ -94,9 +94,10 @@ def samples_of(shape) -> int:
 
 class ClockSampler:
     """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe).  The sampler is started
-    before the warm-up (nvidia-smi needs a few hundred ms to come up, longer on an 8-GPU box) and the samples are cut to
-    the timed window by their timestamps; if the window is shorter than the sampling period the samples taken under the
-    identical warm-up load are used and the record says so."""
+    while the GPU is still idle (nvidia-smi needs a few hundred ms to come up, longer on an 8-GPU box; no load is added
+    before the timed region: a long pre-load pushes the part into its 1 kW power cap, 1965 -> ~1630 MHz) and the samples
+    are cut to the timed window by their timestamps; if the window is shorter than the sampling period, all samples since
+    the start are used and the record says so."""
 
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -159,7 +160,7 @@ class ClockSampler:
         window = "timed region"
         sm, mx, reasons = parse(inside)
         if not sm:
-            window = "warm-up + timed region (the timed region is shorter than the sampling period)"
+            window = "start of the run .. timed region (the timed region is shorter than the sampling period)"
             sm, mx, reasons = parse(self.lines)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
@@ -380,6 +381,8 @@ def main() -> None:
         return float(t.item())
 
     _dbg("process group up")
+    sampler = ClockSampler(local)
+    sampler.start()                            # nvidia-smi needs a few hundred ms to come up: start it while the GPU is idle
     B = args.batch or cfg["shape"][0]
     shape = (B,) + tuple(cfg["shape"][1:])
     dtype = DT[cfg["dtype"]]
@@ -389,18 +392,12 @@ def main() -> None:
     fwd = make_forward(wt, cfg)
     inv = make_inverse(wt, cfg)
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    t_w = time.time()
     for _ in range(max(args.warmup, 3)):
         out = fwd(x)
     alg = nbytes([x]) + nbytes(flat(out))     # algorithmic bytes: input read once + every returned coefficient written once
     d2h_bytes = nbytes(flat(out))
-    torch.cuda.synchronize(dev)
-    while time.time() - t_w < 0.6:            # let nvidia-smi come up under the same load (not timed)
-        out = fwd(x)
-        torch.cuda.synchronize(dev)
     del out
+    torch.cuda.synchronize(dev)
 
     _dbg("warm-up done")
     _native.launch_count_reset()
