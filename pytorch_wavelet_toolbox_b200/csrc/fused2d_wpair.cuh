@@ -524,7 +524,9 @@ bool try_wpair<float>(const float* x, int64_t B, int H, int W, int64_t x_bs, int
                       uint64_t* launches, cudaError_t* err) {
     // Opt-in (WTB200_WPAIR=1 / wt_set_knob("WPAIR", 1)): parity green, 19 % less DRAM traffic than one launch per level,
     // but issue-bound (1.7 IPC/SM at 12 independent warps per SM) -- 1.84 ms vs 1.78-1.85 ms for the first two levels
-    // of 64 x 4096^2, i.e. no faster (profiles/r02_wpair_*).
+    // of 64 x 4096^2, i.e. no faster (profiles/r02_wpair_*).  Running it on part of the batch concurrently with the
+    // per-level kernels on the rest (different bottlenecks) was measured too: 2.01-2.08 ms vs 1.87 ms
+    // (profiles/r02_ab_wpair_hybrid.json).
     if (!knob_on(K_WPAIR) || knob_on(K_NO_WPAIR) || knob_on(K_DISABLE_FUSED)) return false;
     switch (L) {
         case 2: return launch_fwd2d_wpair_t<2, 3, 12>(x, B, H, W, x_bs, x_rs, l1, l2, mode, taps, st, launches, err);

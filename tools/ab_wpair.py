@@ -32,11 +32,10 @@ def main():
     alg = 134612360 * B
     res = {}
     for name, kn, lev in (
-        ("default L4", {}, 4), ("per-level L4", {"NO_WPAIR": 1}, 4),
-        ("var0 L2", {}, 2), ("var1 L2", {"WPAIR_VAR": 1}, 2), ("var2 L2", {"WPAIR_VAR": 2}, 2), ("per-level L2", {"NO_WPAIR": 1}, 2),
-        ("var1 L4", {"WPAIR_VAR": 1}, 4),
-        ("var1 seg96 L2", {"WPAIR_VAR": 1, "WPAIR_SEG": 96}, 2), ("var1 seg200 L2", {"WPAIR_VAR": 1, "WPAIR_SEG": 200}, 2),
-        ("var0 seg96 L2", {"WPAIR_SEG": 96}, 2), ("var0 seg200 L2", {"WPAIR_SEG": 200}, 2),
+        ("default L4", {}, 4), ("wpair L4", {"WPAIR": 1}, 4),
+        ("hybrid 8", {"WPAIR_HYBRID": 8}, 4), ("hybrid 12", {"WPAIR_HYBRID": 12}, 4), ("hybrid 16", {"WPAIR_HYBRID": 16}, 4),
+        ("hybrid 20", {"WPAIR_HYBRID": 20}, 4), ("hybrid 24", {"WPAIR_HYBRID": 24}, 4), ("hybrid 32", {"WPAIR_HYBRID": 32}, 4),
+        ("default L4 again", {}, 4),
     ):
         with _native.knobs(**kn):
             _native.launch_count_reset()
