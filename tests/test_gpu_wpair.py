@@ -128,19 +128,21 @@ def test_headline_configuration_every_image():
 
 
 def test_host_pipeline_real_chunk_size():
-    """fwt._analysis_host_pipeline with its real 256 MB chunks (3 chunks, the last one ragged) against the
-    device-resident path on the same data."""
+    """fwt._analysis_host_pipeline with its real 256 MB chunks (2.25 GB of input: 9 chunks of 64 images) against the
+    device-resident path on the same data, and a mid-size input (cut into ~8 smaller chunks)."""
     from pytorch_wavelet_toolbox_b200 import fwt as F
 
     g = torch.Generator().manual_seed(77)
-    n = (2 * F.HOST_PIPELINE_CHUNK_BYTES + F.HOST_PIPELINE_CHUNK_BYTES // 2) // (1024 * 1024 * 4)
-    x = torch.randn(n, 1024, 1024, generator=g)
-    host = wt.wavedec2(x, "db4", level=3)
-    dev = wt.wavedec2(x.to(DEV), "db4", level=3)
-    for a, b in zip(flatten_coeffs(host), flatten_coeffs(dev)):
-        assert a.device.type == "cpu" and torch.equal(a, b.cpu())
-    for i in (0, n // 2, n - 1):
-        want = flatten_coeffs(P.wavedec2(x[i:i + 1], "db4", level=3))
-        scale = max(float(t.abs().max()) for t in want)
-        for a, b in zip(flatten_coeffs(host), want):
-            assert_close_rel(a[i:i + 1], b, scale=scale, what=f"host pipeline image {i}")
+    for n in (9 * F.HOST_PIPELINE_CHUNK_BYTES // (1024 * 1024 * 4), 100):
+        x = torch.randn(n, 1024, 1024, generator=g)
+        assert x.numel() * 4 >= F.HOST_PIPELINE_MIN_BYTES
+        host = wt.wavedec2(x, "db4", level=3)
+        dev = wt.wavedec2(x.to(DEV), "db4", level=3)
+        for a, b in zip(flatten_coeffs(host), flatten_coeffs(dev)):
+            assert a.device.type == "cpu" and torch.equal(a, b.cpu())
+        for i in (0, n // 2, n - 1):
+            want = flatten_coeffs(P.wavedec2(x[i:i + 1], "db4", level=3))
+            scale = max(float(t.abs().max()) for t in want)
+            for a, b in zip(flatten_coeffs(host), want):
+                assert_close_rel(a[i:i + 1], b, scale=scale, what=f"host pipeline image {i}")
+        del host, dev, x
