@@ -359,6 +359,8 @@ struct MatInvFusedParams {
     int cap;                     // capacity of one approximation buffer
     int hi_cap;                  // capacity of the detail staging area
     T rlo[16], rhi[16];          // rec_lo / rec_hi, un-flipped
+    int vec;                     // matrix_dmma.cuh: bit j-1 = hi[j-1] rows 16-byte aligned, bit 14 = y, bit 15 = lo
+    int rows, batch, cap_lo;     // matrix_dmma.cuh (row-streaming kernel): rows per CTA, batch, coarsest staging size
 };
 
 template <typename T, int L>

@@ -556,16 +556,19 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
         if (allow_fused && !knob_on(K_DISABLE_FUSED)) {
             // group of consecutive unpadded levels -> one fused launch
             int k = 0;
-            // 4 levels per launch while a row is cut into chunks (halo grows with 2^k), all remaining levels (up to
+            // while a row is cut into chunks: 4 levels per launch (float32) or 2 (float64 DMMA cascade: 0.402 ms on
+            // config 4 against 0.441 / 0.430 with 3 / 4, tools/ab_matrix_inv.py); all remaining levels (up to
             // MATF_MAXK) once a whole row fits one chunk -- tools/ab_matrix2.py
-            int kmax = n[l] <= 8192 ? MATF_MAXK : 4;
+            int kmax = n[l] <= 8192 ? MATF_MAXK : (sizeof(T) == 8 && !knob_on(K_NO_DMMA) ? 2 : 4);
             if (knob_is_set(K_MATF_K)) { const int v = (int)knob_val(K_MATF_K, 0); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
             while (l + k < levels && k < kmax && !padded[l + k] && !(n[l + k] & 1) &&
                    (k == 0 || n[l + k] == n[l + k - 1] / 2))
                 ++k;
             if (k >= 2) {
                 const bool last = (l + k == levels);
-                T* lo_dst = last ? (T*)lo_out : ping[(l + k - 1) & 1];
+                // the scratch half that is not this group's source (groups of even depth would otherwise write the
+                // approximation over the buffer they are reading)
+                T* lo_dst = last ? (T*)lo_out : (src == ping[0] ? ping[1] : ping[0]);
                 const int64_t lo_ds = last ? lo_stride : n[l + k - 1] / 2;
                 cudaError_t e = cudaSuccess;
                 bool launched = false;
@@ -594,7 +597,7 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
         p.batch = batch; p.n = n[l]; p.n_in = n[l] - (padded[l] ? 1 : 0);
         p.hi = (T*)hi_out[l]; p.hi_stride = hi_stride[l];
         const bool last = (l == levels - 1);
-        p.lo = last ? (T*)lo_out : ping[l & 1];
+        p.lo = last ? (T*)lo_out : (src == ping[0] ? ping[1] : ping[0]);
         p.lo_stride = last ? lo_stride : n[l] / 2;
         p.L = L; p.shift = L / 2 + (L % 2); p.odd_mode = odd_mode;
         p.nb_top = nbt[l]; p.nb_bot = nbb[l]; p.w_left = wt[l]; p.w_right = wb[l];
@@ -665,10 +668,15 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
     }
     for (int l = levels - 1; l >= 0; --l) {
         if (allow_fused && !knob_on(K_DISABLE_FUSED)) {
-            // group of levels l, l-1, ..., l-k+1 whose intermediate results are not trimmed -> one launch
-            // default 1 = per-level kernels: on config 4 the fused synthesis kernel (0.79 ms) is slower than
-            // twelve register-blocked per-level launches (0.57 ms); WTB200_MATI_K >= 2 opts in
-            int kmax = 1;
+            // group of levels l, l-1, ..., l-k+1 whose intermediate results are not trimmed -> one launch.
+            // float64: the synthesis cascade on the FP64 tensor cores (matrix_dmma.cuh), 2 levels per launch -- deeper
+            // cascades save HBM traffic but lose more to barriers and thin coarse levels (config 4: 0.316 ms with 2,
+            // 0.386 with 3, 0.366 with 4 levels per launch, 0.336 with 2 + one launch for all levels whose row fits
+            // a CTA; tools/ab_matrix_inv.py).  float32: per-level kernels by default -- the scalar fused synthesis
+            // kernel (0.79 ms) is slower than twelve register-blocked per-level launches (0.57 ms).
+            // WTB200_MATI_K sets the number of levels per launch for both.
+            const bool dmma = sizeof(T) == 8 && !knob_on(K_NO_DMMA);
+            int kmax = dmma ? 2 : 1;
             if (knob_is_set(K_MATI_K)) { const int v = (int)knob_val(K_MATI_K, 0); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
             int k = 1;
             while (k < kmax && l - k >= 0 && next_len[l - k + 1] == n[l - k + 1] && n[l - k] == 2 * n[l - k + 1]) ++k;
@@ -680,9 +688,21 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
                 T* dst = last ? (T*)y : ping[pp];
                 const int64_t dst_stride = last ? ys : (keep4 <= n[0] ? keep4 : keep0);
                 cudaError_t e = cudaSuccess;
-                if ((keep0 == n[lf] || keep0 == n[lf] - 1) &&
-                    launch_mat_inv_fused<T>(L, k, n + lf, keep0, nbt + lf, nbb + lf, wt + lf, wb + lf, bptr + 4 * lf, src,
-                                            src_stride, hi_in + lf, hi_stride + lf, batch, dst, dst_stride, rlo, rhi, st, &e)) {
+                bool launched = false;
+                if (keep0 == n[lf] || keep0 == n[lf] - 1) {
+                    if constexpr (sizeof(T) == 8) {
+                        if (dmma)
+                            launched = launch_mat_inv_dmma(L, k, n + lf, keep0, nbt + lf, nbb + lf, wt + lf, wb + lf,
+                                                           (const double* const*)(bptr + 4 * lf), (const double*)src, src_stride,
+                                                           hi_in + lf, hi_stride + lf, batch, (double*)dst, dst_stride, rlo, rhi,
+                                                           st, &e);
+                    }
+                    if (!launched && knob_is_set(K_MATI_K))
+                        launched = launch_mat_inv_fused<T>(L, k, n + lf, keep0, nbt + lf, nbb + lf, wt + lf, wb + lf,
+                                                           bptr + 4 * lf, src, src_stride, hi_in + lf, hi_stride + lf, batch,
+                                                           dst, dst_stride, rlo, rhi, st, &e);
+                }
+                if (launched) {
                     g_launches.fetch_add(1, std::memory_order_relaxed);
                     if (e != cudaSuccess) return cuda_fail(e, "mat_inv_fused_kernel");
                     src = dst; src_stride = dst_stride;

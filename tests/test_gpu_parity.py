@@ -11,6 +11,7 @@ import pytest
 import torch
 
 import pytorch_wavelet_toolbox_b200 as wt
+from pytorch_wavelet_toolbox_b200 import _native
 from conftest import TOL, assert_close_rel, flatten_coeffs
 from oracle import ptwt_port as P
 
@@ -283,6 +284,28 @@ def test_matrix_round_trip_and_orthogonality_config4_shape():
     inv(cs)
     eye = inv.sparse_ifwt_operator.to_dense() @ op
     assert (eye - torch.eye(64, dtype=torch.float64)).abs().max() < 1e-8
+
+
+@pytest.mark.parametrize("dtype,n,batch", [(torch.float64, 65536, 640), (torch.float32, 262144, 96)])
+def test_matrix_level_groups_never_run_in_place(dtype, n, batch):
+    """Long rows are analysed in several fused launches whose intermediate approximations ping-pong between the two
+    halves of the scratch buffer.  Regression: a group of even depth in the middle of the chain used to get its own
+    source half as destination (float64 with 2 levels per launch; float32 from 262144 samples on), which only shows
+    with enough rows in flight.  The fused chain must agree with the per-level kernels, preserve energy and invert."""
+    g = torch.Generator(device=DEV).manual_seed(19)
+    x = torch.randn(batch, n, generator=g, device=DEV, dtype=dtype)
+    fw = wt.MatrixWavedec("db6")
+    c = fw(x)
+    with _native.knobs(DISABLE_FUSED=1):
+        want = wt.MatrixWavedec("db6")(x)
+    scale = max(float(t.abs().max()) for t in want)
+    for a, b in zip(c, want):
+        assert_close_rel(a, b, scale=scale, what=f"fused groups vs per-level kernels, n={n} {dtype}")
+    e_in = float((x.double() ** 2).sum())
+    e_out = sum(float((t.double() ** 2).sum()) for t in c)
+    assert abs(e_in - e_out) / e_in < (1e-12 if dtype == torch.float64 else 1e-5)
+    rec = wt.MatrixWaverec("db6")(c)
+    assert float((rec - x).abs().max()) < (1e-10 if dtype == torch.float64 else 2e-4)
 
 
 def test_full_size_properties_config2():
@@ -636,6 +659,36 @@ def test_fused_matrix_synthesis_kernel_when_enabled(knob):
         want = P.MatrixWaverec(wav)(want_c)
         got = wt.MatrixWaverec(wav)([t.to(DEV) for t in want_c])
         assert_close_rel(got, want, scale=float(want.abs().max()), what=f"fused synthesis {wav} n={n} L{level}")
+
+
+@pytest.mark.parametrize("rows", [None, 0, -1, -3])
+def test_matrix_synthesis_on_the_fp64_tensor_cores(knob, rows):
+    """float64 MatrixWaverec runs groups of levels as one DMMA cascade (matrix_dmma.cuh): the row-streaming kernel
+    (TMA bulk staging, WTB200_MATI_ROWS < 0 forces that many rows per CTA) or, for unaligned / odd band lengths and MATI_ROWS=0, the
+    chunk-per-CTA kernel.  Both must agree with the oracle where the oracle's dense operators fit, with the per-level
+    kernels (NO_DMMA) everywhere, and invert MatrixWavedec."""
+    if rows is not None:
+        knob("MATI_ROWS", rows)
+    g = torch.Generator().manual_seed(84 + abs(rows or 0))
+    for wav, n, level, bs in (("haar", 64, 3, 5), ("db2", 96, None, 7), ("db3", 250, 4, 7), ("db4", 1000, None, 4),
+                              ("sym5", 4096, 7, 7), ("db6", 5001, None, 3), ("db7", 20000, 5, 7), ("db8", 8192, None, 7),
+                              ("db6", 65536, None, 7), ("db4", 65536, 2, 5)):
+        x = torch.randn((bs, n), generator=g, dtype=torch.float64)
+        co = wt.MatrixWavedec(wav, level)(x.to(DEV))
+        got = wt.MatrixWaverec(wav)(co)
+        with _native.knobs(NO_DMMA=1):
+            per_level = wt.MatrixWaverec(wav)(co)
+        tag = f"dmma synthesis rows={rows} {wav} n={n} level={level}"
+        assert_close_rel(got, per_level, scale=float(per_level.abs().max()), what=tag + " vs per-level kernels")
+        assert float((got[..., :n].cpu() - x).abs().max()) < 1e-9, tag + " round trip"
+        if n <= 4096:
+            want = P.MatrixWaverec(wav)([t.cpu() for t in co])
+            assert_close_rel(got, want.contiguous(), scale=float(want.abs().max()), what=tag + " vs oracle")
+    # strided views of a packed buffer (rows not 16-byte aligned -> chunk-per-CTA kernel with 8-byte copies)
+    x = torch.randn((6, 1024), generator=g, dtype=torch.float64)
+    co = wt.MatrixWavedec("db4", 4)(x.to(DEV))
+    odd = [torch.empty(6, t.shape[-1] + 1, device=DEV, dtype=torch.float64)[:, 1:].copy_(t) for t in co]
+    assert float((wt.MatrixWaverec("db4")(odd).cpu() - x).abs().max()) < 1e-10
 
 
 @pytest.mark.parametrize("tile", ["0", "1", "2"])
