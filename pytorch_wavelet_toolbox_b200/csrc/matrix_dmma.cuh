@@ -274,7 +274,8 @@ static bool launch_mat_fwd_dmma(int L, int k, const int64_t* n, const int32_t* n
     const int nchunks = (nk + tk - 1) / tk;
     int cpc = (int)knob_val(K_MATF_CPC, 8);
     if (cpc < 1) cpc = 1;
-    while (cpc > 1 && (int64_t)((nchunks + cpc - 1) / cpc) * batch < 4 * 148) cpc /= 2;
+    const int64_t min_ctas = knob_val(K_MATF_MINCTAS, 4 * 148);
+    while (cpc > 1 && (int64_t)((nchunks + cpc - 1) / cpc) * batch < min_ctas) cpc /= 2;
     p.cpc = cpc;
     dim3 grid((nchunks + cpc - 1) / cpc, (unsigned)batch);
     const int nt = knob_val(K_MATF_NT, 128) == 256 ? 256 : 128;
@@ -300,6 +301,273 @@ static bool launch_mat_fwd_dmma(int L, int k, const int64_t* n, const int32_t* n
     return true;
 }
 
+
+// ==========================================================================================
+// The analysis cascade again, laid out like the synthesis kernel below (which reaches 81 % of the HBM peak on its
+// finest launch where the kernel above reaches 64 %): one chunk per CTA, every level input kept as two POLYPHASE arrays
+// (even samples | odd samples, the odd array two doubles further in the bank pattern), the DATA in the A operand and
+// the polyphase FILTER matrix in the B operand:
+//
+//     D[8 groups x (2 bands x 4 outputs)] = A[8 x 4 KS] * B[4 KS x 8],
+//         A[g][u = (phase, v)] = x_phase[i0 + 4 g + v - C_phase],   B[u][(band, s)] = f_band[2 (v - s) + (phase ^ b)]
+//
+// so that the A fragment of a k-step is one conflict-free 64-bit shared load per lane and the D fragment of a lane is
+// an output PAIR of one band: the approximation pair goes to the next level's even / odd arrays (two conflict-free
+// 64-bit stores), the detail pair to HBM as one 128-bit store (a quarter-warp writes 128 contiguous bytes).
+// ==========================================================================================
+template <int L, int NT>
+__global__ void __launch_bounds__(NT) mat_fwd_dmma2_kernel(const __grid_constant__ MatFusedParams<double> p) {
+    constexpr int H = L / 2, HL = H - 1, HR = H;
+    constexpr int B1 = HL & 1, AA = HL >> 1;
+    constexpr int CE = AA, CO = AA + B1;          // x[2 i - HL + m]: even phase starts at i - CE, odd phase at i - CO
+    constexpr int KS = (H + 4) / 2;               // k-steps: H + 3 window positions of each phase, padded to even
+    constexpr int OFFO = B1 ? 3 : 2;              // odd array: two doubles further in the bank pattern (CO - CE = B1)
+    constexpr int NW = NT / 32;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int h0 = p.cap0 / 2 + 8, hA = p.cap0 / 4 + 8, hB = p.cap0 / 8 + 8;   // capacity of one phase array
+    double* buf0 = reinterpret_cast<double*>(smem_raw);
+    double* bufA = buf0 + 2 * h0 + 4;
+    double* bufB = bufA + 2 * hA + 4;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    const int K = p.k;
+    const int chunk = blockIdx.x;
+    const double* __restrict__ xb = p.x + (int64_t)b * p.x_stride;
+
+    __shared__ int s_lo[MATF_MAXK + 1], s_hi[MATF_MAXK + 1];
+    if (tid == 0) {
+        int lo_j = chunk * p.tk, hi_j = min(lo_j + p.tk, p.n[K]);
+        s_lo[K] = lo_j; s_hi[K] = hi_j;
+        for (int j = K; j >= 1; --j) {
+            const int half = p.n[j];
+            int lo = 2 * lo_j - HL, hi = 2 * (hi_j - 1) + HR + 1;
+            if (lo_j < p.nb_top[j - 1]) lo = 0, hi = max(hi, p.w_left[j - 1]);
+            if (hi_j > half - p.nb_bot[j - 1]) hi = p.n[j - 1], lo = min(lo, p.n[j - 1] - p.w_right[j - 1]);
+            lo = max(lo, 0) & ~3;
+            hi = min(hi, p.n[j - 1]);
+            s_lo[j - 1] = lo_j = lo;
+            s_hi[j - 1] = hi_j = hi;
+        }
+    }
+    __syncthreads();
+
+    // level-0 samples -> polyphase arrays (8-byte cp.async: thread parity = phase, NT is even)
+    {
+        const int s0 = s_lo[0], cnt = s_hi[0] - s0;
+        double* dst = (tid & 1) ? buf0 + h0 + OFFO : buf0;
+        for (int q = tid; q < cnt; q += NT) {
+            const unsigned d = (unsigned)__cvta_generic_to_shared(dst + (q >> 1));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(xb + s0 + q) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+
+    // B fragment (the polyphase filter matrix): lane holds B[k = lane % 4][n = lane / 4] of k-step e
+    double bfrag[KS];
+    {
+        const int nn = lane >> 2, k = lane & 3, band = nn >> 2, s = nn & 3, par = k & 1;
+#pragma unroll
+        for (int e = 0; e < KS; ++e) {
+            const int w = 2 * e + (k >> 1) - s;
+            const int tap = 2 * w + (par ^ B1);
+            bfrag[e] = (w >= 0 && w < H) ? (band ? p.fhi[tap] : p.flo[tap]) : 0.0;
+        }
+    }
+    const int a_par = lane & 1;
+    const int a_off = 4 * (lane >> 2) + ((lane & 3) >> 1) - (a_par ? CO : CE);
+    const int out_band = (lane & 3) >> 1;
+    const int out_off = 4 * (lane >> 2) + 2 * (lane & 1);  // D fragment: outputs i0 + out_off, + 1 of band out_band
+
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+
+    double* in = buf0;
+    int hin = h0;
+    double* nxt = bufA;
+    int hnx = hA;
+#pragma unroll 1
+    for (int j = 1; j <= K; ++j) {
+        const int half = p.n[j], nprev = p.n[j - 1];
+        const int in0 = s_lo[j - 1], in_cnt = s_hi[j - 1] - in0;
+        const int cnt_e = (in_cnt + 1) >> 1, cnt_o = in_cnt >> 1, q0 = in0 >> 1;
+        const int o0 = s_lo[j], o1 = s_hi[j];
+        const int own0 = (chunk * p.tk) << (K - j), own1 = min(((chunk + 1) * p.tk) << (K - j), half);
+        const int nbt = p.nb_top[j - 1], nbb = p.nb_bot[j - 1];
+        double* __restrict__ hib = p.hi[j - 1] + (int64_t)b * p.hi_stride[j - 1];
+        double* __restrict__ lob = p.lo + (int64_t)b * p.lo_stride;
+        const bool last = j == K;
+        const bool vec_st = out_band ? ((p.vec >> (j - 1)) & 1) : ((p.vec >> 15) & 1);
+        const double* xe = in;
+        const double* xo = in + hin + OFFO;
+        double* nxe = nxt;
+        double* nxo = nxt + hnx + OFFO;
+        double* __restrict__ gout = out_band ? hib : lob;
+
+        const int ntiles = (o1 - o0 + 31) >> 5;
+        const int lo_all = max(nbt, o0), hi_all = min(half - nbb, o1);
+        int t_lo, t_hi;
+        {
+            const int need0 = max(lo_all - o0, q0 + CO - o0);
+            t_lo = need0 > 0 ? (need0 + 31) >> 5 : 0;
+            const int lim_in = cnt_o - 28 - 2 * KS + CE + q0 - o0;
+            t_hi = min((hi_all - o0) >> 5, lim_in >= 0 ? (lim_in >> 5) + 1 : 0);
+            t_hi = max(min(t_hi, ntiles), 0);
+            t_lo = min(t_lo, t_hi);
+        }
+        const double* band = a_par ? xo : xe;
+        const int cnt_p = a_par ? cnt_o : cnt_e;
+        auto generic_tile = [&](const int t) {
+            const int i0 = o0 + 32 * t;
+            const int rel0 = i0 + a_off - q0;
+            double d0 = 0.0, d1 = 0.0;
+            // samples clamped into the staged range: only outputs that the corner-block code below overwrites, or that
+            // lie beyond o1, can see a clamped value
+#pragma unroll
+            for (int e = 0; e < KS; ++e) {
+                const int rel = min(max(rel0 + 2 * e, 0), cnt_p - 1);
+                dmma_m8n8k4(d0, d1, band[rel], bfrag[e]);
+            }
+            const int ia = i0 + out_off;
+            if (out_band == 0 && !last) {
+                if (ia < o1) nxe[(ia - o0) >> 1] = d0;
+                if (ia + 1 < o1) nxo[(ia - o0) >> 1] = d1;
+            } else {
+                if (ia >= own0 && ia < own1 && ia >= nbt && ia < half - nbb) gout[ia] = d0;
+                if (ia + 1 >= own0 && ia + 1 < own1 && ia + 1 >= nbt && ia + 1 < half - nbb) gout[ia + 1] = d1;
+            }
+        };
+        for (int t = warp; t < t_lo; t += NW) generic_tile(t);
+        for (int t = t_hi + warp; t < ntiles; t += NW) generic_tile(t);
+        {
+            const int tf = t_lo + warp;
+            int ia = o0 + 32 * tf + out_off;
+            const double* src = band + (o0 + 32 * tf + a_off - q0);
+            double* de = nxe + ((ia - o0) >> 1);
+            double* dod = nxo + ((ia - o0) >> 1);
+            double* dgl = gout + ia;
+            const bool to_smem = out_band == 0 && !last;
+            for (int t = tf; t < t_hi; t += NW) {
+                double v[KS];
+#pragma unroll
+                for (int e = 0; e < KS; ++e) v[e] = src[2 * e];
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int e = 0; e < KS; ++e) dmma_m8n8k4(d0, d1, v[e], bfrag[e]);
+                if (to_smem) {
+                    *de = d0; *dod = d1;
+                } else if (ia >= own0 && ia + 1 < own1) {
+                    if (vec_st) {
+                        *reinterpret_cast<double2*>(dgl) = make_double2(d0, d1);
+                    } else {
+                        dgl[0] = d0; dgl[1] = d1;
+                    }
+                } else if (ia >= own0 && ia < own1) {
+                    dgl[0] = d0;
+                }
+                src += 32 * NW; de += 16 * NW; dod += 16 * NW; dgl += 32 * NW; ia += 32 * NW;
+            }
+        }
+        __syncthreads();
+        // ---- corner blocks: the dense orthogonalised boundary rows (the CTAs at the two ends of the row) -------
+        if (o0 < nbt || o1 > half - nbb) {
+            const int nt_ = max(min(o1, nbt) - o0, 0);
+            const int b0 = max(o0, half - nbb), nb_ = max(o1 - b0, 0);
+            for (int q = tid; q < 2 * (nt_ + nb_); q += NT) {
+                const int bnd = q & 1, r = q >> 1;
+                const int ii = r < nt_ ? o0 + r : b0 + (r - nt_);
+                const bool top = ii < nbt;
+                const int rr = top ? ii : nbt + (ii - (half - nbb));
+                const int w = top ? p.w_left[j - 1] : p.w_right[j - 1];
+                const int s0 = (top ? 0 : nprev - w) - in0;
+                const double* __restrict__ blk = (top ? (bnd ? p.hi_left[j - 1] : p.lo_left[j - 1])
+                                                      : (bnd ? p.hi_right[j - 1] : p.lo_right[j - 1])) + rr * w;
+                double acc = 0.0;
+                for (int c = 0; c < w; ++c) {
+                    const int pos = s0 + c;
+                    acc = fma(__ldg(blk + c), ((pos & 1) ? xo : xe)[pos >> 1], acc);
+                }
+                if (bnd == 0) {
+                    if (!last) ((((ii - o0) & 1) ? nxo : nxe))[(ii - o0) >> 1] = acc;
+                    else if (ii >= own0 && ii < own1) lob[ii] = acc;
+                } else if (ii >= own0 && ii < own1) {
+                    hib[ii] = acc;
+                }
+            }
+            __syncthreads();
+        }
+        in = nxt; hin = hnx;
+        if (nxt == bufA) { nxt = bufB; hnx = hB; } else { nxt = bufA; hnx = hA; }
+    }
+}
+
+// Host: the polyphase analysis cascade; false = not applicable (caller falls back to the streaming kernel).
+static bool launch_mat_fwd_dmma2(int L, int k, const int64_t* n, const int32_t* nbt, const int32_t* nbb, const int32_t* wl,
+                                 const int32_t* wr, const double* const* blk_ptrs, const double* x, int64_t xs, int64_t batch,
+                                 void* const* hi_out, const int64_t* hi_stride, double* lo_out, int64_t lo_stride,
+                                 const Taps<double>& taps, cudaStream_t st, cudaError_t* err) {
+    *err = cudaSuccess;
+    if ((L & 1) || L < 2 || L > 16 || k < 1 || k > MATF_MAXK || batch > 65535) return false;
+    if (n[0] >= (int64_t(1) << 30)) return false;
+    MatFusedParams<double> p;
+    memset(&p, 0, sizeof(p));
+    p.x = x; p.x_stride = xs; p.k = k;
+    p.n[0] = (int)n[0];
+    int vec = 0;
+    if (!((uintptr_t)lo_out & 15) && !(lo_stride & 1)) vec |= 1 << 15;
+    for (int j = 0; j < k; ++j) {
+        if (n[j] & 1) return false;
+        p.n[j + 1] = (int)(n[j] / 2);
+        if (j + 1 < k && n[j + 1] != n[j] / 2) return false;
+        p.hi[j] = (double*)hi_out[j]; p.hi_stride[j] = hi_stride[j];
+        if (!((uintptr_t)hi_out[j] & 15) && !(hi_stride[j] & 1)) vec |= 1 << j;
+        p.nb_top[j] = nbt[j]; p.nb_bot[j] = nbb[j]; p.w_left[j] = wl[j]; p.w_right[j] = wr[j];
+        p.lo_left[j] = blk_ptrs[4 * j]; p.lo_right[j] = blk_ptrs[4 * j + 1];
+        p.hi_left[j] = blk_ptrs[4 * j + 2]; p.hi_right[j] = blk_ptrs[4 * j + 3];
+        if (nbt[j] + nbb[j] > p.n[j + 1]) return false;
+    }
+    p.vec = vec;
+    p.lo = lo_out; p.lo_stride = lo_stride;
+    for (int q = 0; q < L; ++q) { p.flo[q] = taps.lo[L - 1 - q]; p.fhi[q] = taps.hi[L - 1 - q]; }
+    const int nk = p.n[k];
+    int chunk0 = 2048;
+    if (knob_is_set(K_MATF_CHUNK)) { const int v = (int)knob_val(K_MATF_CHUNK, 0); if (v >= 64 && v <= 16384) chunk0 = v; }
+    if (n[0] <= 8192 && n[0] > chunk0 && k > 2) chunk0 = (int)n[0];   // deep cascades of short rows: one CTA per row
+    int tk = chunk0 >> k;
+    if (tk < 4) tk = 4;
+    tk = (tk + 3) & ~3;
+    if (tk > nk) tk = (nk + 3) & ~3;
+    p.tk = tk;
+    int cap0 = (tk << k) + ((L + 6) << k) + 64;
+    if (cap0 > p.n[0] + 16) cap0 = p.n[0] + 16;
+    cap0 = (cap0 + 31) & ~31;
+    p.cap0 = cap0;
+    const size_t smem = (size_t)((cap0 + 16 + 4) + (cap0 / 2 + 16 + 4) + (cap0 / 4 + 16 + 4)) * sizeof(double);
+    if (smem > 200 * 1024) return false;
+    const int nchunks = (nk + tk - 1) / tk;
+    p.cpc = 1;
+    dim3 grid((unsigned)nchunks, (unsigned)batch);
+    const int nt = knob_val(K_MATF_NT, 128) == 256 ? 256 : 128;
+#define WTB_MD2_LAUNCH(LL, NTT)                                                                        \
+    {                                                                                                  \
+        cudaError_t e = ensure_dyn_smem(mat_fwd_dmma2_kernel<LL, NTT>, 200 * 1024);                    \
+        if (e != cudaSuccess) { *err = e; return true; }                                               \
+        mat_fwd_dmma2_kernel<LL, NTT><<<grid, NTT, smem, st>>>(p);                                     \
+    }
+#define WTB_MD2(LL)                                                                                    \
+    case LL:                                                                                           \
+        if (nt == 128) WTB_MD2_LAUNCH(LL, 128) else WTB_MD2_LAUNCH(LL, 256)                            \
+        break;
+    switch (L) {
+        WTB_MD2(2) WTB_MD2(4) WTB_MD2(6) WTB_MD2(8) WTB_MD2(10) WTB_MD2(12) WTB_MD2(14) WTB_MD2(16)
+        default: return false;
+    }
+#undef WTB_MD2
+#undef WTB_MD2_LAUNCH
+    *err = cudaGetLastError();
+    return true;
+}
 
 // ==========================================================================================
 // MatrixWaverec on the FP64 tensor cores: the synthesis cascade (coarse to fine) of K levels in one launch.
@@ -796,7 +1064,12 @@ static bool launch_mat_inv_dmma(int L, int k, const int64_t* n, int64_t keep0, c
     for (int q = 0; q < L; ++q) { p.rlo[q] = rlo[q]; p.rhi[q] = rhi[q]; }
     int chunk = 2048;                                               // tools/ab_matrix_inv.py
     if (knob_is_set(K_MATI_CHUNK)) { const int v = (int)knob_val(K_MATI_CHUNK, 0); if (v >= 64 && v <= 16384) chunk = v; }
-    if (p.n[0] <= 8192) chunk = p.n[0];                             // coarse groups: one CTA per row
+    if (!knob_is_set(K_MATI_CHUNK)) {
+        // short rows: smaller chunks until the launch has MATI_MINCTAS CTAs
+        const int64_t min_ctas = knob_val(K_MATI_MINCTAS, 0);
+        while (chunk > 256 && ((p.n[0] + chunk - 1) / chunk) * batch < min_ctas) chunk /= 2;
+    }
+    if (chunk > p.n[0] && p.n[0] <= 8192) chunk = p.n[0];
     chunk = (chunk + 63) / 64 * 64;
     if (chunk > p.n[0]) chunk = (p.n[0] + 63) / 64 * 64;
     p.chunk = chunk;

@@ -41,6 +41,7 @@ struct MatFusedParams {
     int cpc;                     // consecutive chunks of one row a CTA streams through
     int cap0;                    // capacity (samples) of the level-0 staging arrays
     T flo[16], fhi[16];          // taps in window order: out[i] = sum_k f[k] a[2i - (L/2-1) + k]
+    int vec;                     // matrix_dmma.cuh (polyphase kernel): bit j = hi[j] rows 16-byte aligned, bit 15 = lo
 };
 
 template <typename T> struct Vec2Of;

@@ -556,10 +556,13 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
         if (allow_fused && !knob_on(K_DISABLE_FUSED)) {
             // group of consecutive unpadded levels -> one fused launch
             int k = 0;
-            // while a row is cut into chunks: 4 levels per launch (float32) or 2 (float64 DMMA cascade: 0.402 ms on
-            // config 4 against 0.441 / 0.430 with 3 / 4, tools/ab_matrix_inv.py); all remaining levels (up to
-            // MATF_MAXK) once a whole row fits one chunk -- tools/ab_matrix2.py
-            int kmax = n[l] <= 8192 ? MATF_MAXK : (sizeof(T) == 8 && !knob_on(K_NO_DMMA) ? 2 : 4);
+            // float32: 4 levels per launch while a row is cut into chunks, all remaining levels (up to MATF_MAXK) once
+            // a whole row fits one chunk (tools/ab_matrix2.py).  float64 (DMMA cascade): 2 levels per launch throughout
+            // -- config 4: 0.355 ms against 0.411 / 0.381 with 3 / 4 and 0.372 with one launch for the short rows
+            // (tools/ab_matrix_inv.py)
+            const bool dmma64 = sizeof(T) == 8 && !knob_on(K_NO_DMMA);
+            int kmax = n[l] <= 8192 ? (int)knob_val(K_MATF_KCOARSE, dmma64 ? 2 : MATF_MAXK) : (dmma64 ? 2 : 4);
+            if (kmax < 1 || kmax > MATF_MAXK) kmax = MATF_MAXK;
             if (knob_is_set(K_MATF_K)) { const int v = (int)knob_val(K_MATF_K, 0); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
             while (l + k < levels && k < kmax && !padded[l + k] && !(n[l + k] & 1) &&
                    (k == 0 || n[l + k] == n[l + k - 1] / 2))
@@ -574,7 +577,12 @@ static int matrix_fwd_t(int levels, int L, const double* dlo, const double* dhi,
                 bool launched = false;
                 if constexpr (sizeof(T) == 8) {
                     // float64: the band contraction on the FP64 tensor cores (matrix_dmma.cuh)
-                    if (!knob_on(K_NO_DMMA))
+                    // (matrix_dmma.cuh: the polyphase kernel, WTB200_MATF_VARIANT=1 = the streaming kernel)
+                    if (!knob_on(K_NO_DMMA) && knob_val(K_MATF_VARIANT, 2) != 1)
+                        launched = launch_mat_fwd_dmma2(L, k, n + l, nbt + l, nbb + l, wt + l, wb + l,
+                                                        (const double* const*)(bptr + 4 * l), (const double*)src, src_stride, batch,
+                                                        hi_out + l, hi_stride + l, (double*)lo_dst, lo_ds, taps, st, &e);
+                    if (!launched && !knob_on(K_NO_DMMA))
                         launched = launch_mat_fwd_dmma(L, k, n + l, nbt + l, nbb + l, wt + l, wb + l,
                                                        (const double* const*)(bptr + 4 * l), (const double*)src, src_stride, batch,
                                                        hi_out + l, hi_stride + l, (double*)lo_dst, lo_ds, taps, st, &e);
@@ -679,7 +687,10 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
             int kmax = dmma ? 2 : 1;
             if (knob_is_set(K_MATI_K)) { const int v = (int)knob_val(K_MATI_K, 0); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
             int k = 1;
-            while (k < kmax && l - k >= 0 && next_len[l - k + 1] == n[l - k + 1] && n[l - k] == 2 * n[l - k + 1]) ++k;
+            const int64_t merge_n = dmma && !knob_is_set(K_MATI_K) ? knob_val(K_MATI_MERGE_N, 0) : 0;
+            while (l - k >= 0 && next_len[l - k + 1] == n[l - k + 1] && n[l - k] == 2 * n[l - k + 1] &&
+                   (k < kmax || (k < MATF_MAXK && n[l - k] <= merge_n)))
+                ++k;
             if (k >= 2) {
                 const int lf = l - k + 1;  // finest level of the group
                 const bool last = (lf == 0);

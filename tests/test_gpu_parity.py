@@ -661,6 +661,38 @@ def test_fused_matrix_synthesis_kernel_when_enabled(knob):
         assert_close_rel(got, want, scale=float(want.abs().max()), what=f"fused synthesis {wav} n={n} L{level}")
 
 
+@pytest.mark.parametrize("variant,nt", [(2, 128), (2, 256), (1, 128)])
+def test_matrix_analysis_on_the_fp64_tensor_cores(knob, variant, nt):
+    """float64 MatrixWavedec runs groups of levels as one DMMA cascade (matrix_dmma.cuh): the polyphase kernel (default)
+    or the streaming kernel (WTB200_MATF_VARIANT=1).  Both must agree with the oracle where its dense operators fit and
+    with the per-level kernels (DISABLE_FUSED) everywhere, for every filter length, odd lengths and unaligned rows."""
+    knob("MATF_VARIANT", variant)
+    knob("MATF_NT", nt)
+    g = torch.Generator().manual_seed(85 + variant)
+    for wav, n, level, bs in (("haar", 64, 3, 5), ("db2", 96, None, 7), ("db3", 250, 4, 7), ("db4", 1000, None, 4),
+                              ("sym5", 4096, 7, 7), ("db6", 5001, None, 3), ("db7", 20000, 5, 7), ("db8", 8192, None, 7),
+                              ("db6", 65536, None, 7), ("db5", 40000, 3, 9)):
+        x = torch.randn((bs, n), generator=g, dtype=torch.float64)
+        got = wt.MatrixWavedec(wav, level)(x.to(DEV))
+        with _native.knobs(DISABLE_FUSED=1):
+            per_level = wt.MatrixWavedec(wav, level)(x.to(DEV))
+        tag = f"dmma analysis variant={variant} nt={nt} {wav} n={n} level={level}"
+        scale = max(float(t.abs().max()) for t in per_level)
+        assert len(got) == len(per_level)
+        for a, b in zip(got, per_level):
+            assert_close_rel(a, b, scale=scale, what=tag + " vs per-level kernels")
+        if n <= 4096:
+            want = P.MatrixWavedec(wav, level)(x)
+            for a, b in zip(got, want):
+                assert_close_rel(a, b.contiguous(), scale=scale, what=tag + " vs oracle")
+    # rows that are not 16-byte aligned (a strided view): scalar detail stores
+    x = torch.randn((6, 1025), generator=g, dtype=torch.float64).to(DEV)[:, 1:]
+    got = wt.MatrixWavedec("db4", 4)(x)
+    want = P.MatrixWavedec("db4", 4)(x.cpu().contiguous())
+    for a, b in zip(got, want):
+        assert_close_rel(a, b.contiguous(), scale=float(want[0].abs().max()), what="unaligned rows")
+
+
 @pytest.mark.parametrize("rows", [None, 0, -1, -3])
 def test_matrix_synthesis_on_the_fp64_tensor_cores(knob, rows):
     """float64 MatrixWaverec runs groups of levels as one DMMA cascade (matrix_dmma.cuh): the row-streaming kernel

@@ -19,6 +19,14 @@ for wav, n, lev, bs in itertools.product(*[()] * 4) if not SWEEP else itertools.
         co = fw(x)
     except Exception as e:  # too many levels for this length etc.
         continue
+    with _native.knobs(DISABLE_FUSED=1):
+        co_ref = wt.MatrixWavedec(wav, level=lev)(x)
+    with _native.knobs(MATF_VARIANT=1):
+        co_v1 = wt.MatrixWavedec(wav, level=lev)(x)
+    ferr = max(max((a - b).abs().max().item(), (c - b).abs().max().item()) for a, b, c in zip(co, co_ref, co_v1))
+    if not ferr < 1e-12:
+        bad += 1
+        print(f"FORWARD MISMATCH {wav} n={n} level={lev} batch={bs}: {ferr:.3e}", flush=True)
     iv = wt.MatrixWaverec(wav)
     y = iv(co)
     with _native.knobs(NO_DMMA=1):
@@ -61,17 +69,17 @@ def timeit(tag, **kn):
 
 
 timeit("per-level", NO_DMMA=1)
-for kf, chunk, nt in itertools.product((2, 3, 4), (1024, 1536, 2048, 3072), (128, 256)):
-    timeit(f"dmma kfine{kf} chunk{chunk} nt{nt}", MATI_KFINE=kf, MATI_CHUNK=chunk, MATI_NT=nt)
-timeit("dmma rows4 kfine2 chunk1024", MATI_ROWS=4, MATI_CHUNK=1024)
-timeit("dmma rows4 kfine2 chunk2048", MATI_ROWS=4, MATI_CHUNK=2048)
+timeit("dmma default")
 
-# the analysis side: levels per launch
+# the analysis side
 fw = wt.MatrixWavedec("db6")
 iv = fw
 co = x
-timeit("forward default")
-for k, chunk, cpc in itertools.product((2, 3, 4), (2048, 4096), (4, 8)):
-    timeit(f"forward k{k} chunk{chunk} cpc{cpc}", MATF_K=k, MATF_CHUNK=chunk, MATF_CPC=cpc)
+timeit("forward default (polyphase kernel)")
+timeit("forward streaming kernel", MATF_VARIANT=1)
+for chunk, kc, nt in itertools.product((1024, 2048, 4096), (2, 4, 8), (128, 256)):
+    timeit(f"forward polyphase chunk{chunk} kcoarse{kc} nt{nt}", MATF_CHUNK=chunk, MATF_KCOARSE=kc, MATF_NT=nt)
+timeit("forward polyphase k=3", MATF_K=3)
+timeit("forward polyphase k=4", MATF_K=4)
 Path("gpurun_out").mkdir(exist_ok=True)
 Path("gpurun_out/ab_matrix_inv.json").write_text(json.dumps(res, indent=1))
