@@ -10,6 +10,14 @@
 
 namespace wtb {
 
+// Matrix FWT (matrix_dmma.cuh, matrix_fused.cuh; defaults from tools/ab_matrix2.py / tools/ab_matrix_inv.py):
+//   NO_DMMA          float64 without the FP64 tensor-core cascades (scalar fused / per-level kernels)
+//   MATF_VARIANT     1 = streaming DMMA analysis kernel instead of the polyphase one
+//   MATF_K / MATI_K  levels per launch (analysis / synthesis);  MATF_KCOARSE the same for rows <= 8192 samples
+//   MATF_CHUNK / MATI_CHUNK   finest-level samples per CTA;  MATF_NT / MATI_NT  threads per CTA (128 | 256)
+//   MATF_CPC, MATF_MINCTAS    streaming kernels: chunks per CTA and the CTA count it is lowered for
+//   MATI_ROWS        > 0 row-streaming synthesis kernel with at most that many rows per CTA, < 0 exactly, 0 off
+//   MATI_MINCTAS, MATI_MERGE_N   short rows: halve the chunk below this CTA count / merge levels of rows <= N
 #define WTB_KNOB_LIST(X)                                                                                     \
     X(DISABLE_FUSED) X(NO_FFMA2) X(CHUNK) X(STREAMS) X(SPLIT) X(FWD2D_VARIANT) X(MEGA) X(MEGA_SEG) X(MEGA_RING) \
     X(MEGA_NOHINTS) X(ENABLE_PAIR) X(PAIR_TW2) X(FWD3D_TILE) X(CONVF_CHUNK) X(CONVF_K) X(MATF_CHUNK) X(MATI_CHUNK) \

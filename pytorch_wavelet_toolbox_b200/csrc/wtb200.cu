@@ -687,7 +687,7 @@ static int matrix_inv_t(int levels, int L, const double* rlo, const double* rhi,
             int kmax = dmma ? 2 : 1;
             if (knob_is_set(K_MATI_K)) { const int v = (int)knob_val(K_MATI_K, 0); if (v >= 1 && v <= MATF_MAXK) kmax = v; }
             int k = 1;
-            const int64_t merge_n = dmma && !knob_is_set(K_MATI_K) ? knob_val(K_MATI_MERGE_N, 0) : 0;
+            const int64_t merge_n = dmma && !knob_is_set(K_MATI_K) ? knob_val(K_MATI_MERGE_N, 1024) : 0;
             while (l - k >= 0 && next_len[l - k + 1] == n[l - k + 1] && n[l - k] == 2 * n[l - k + 1] &&
                    (k < kmax || (k < MATF_MAXK && n[l - k] <= merge_n)))
                 ++k;
