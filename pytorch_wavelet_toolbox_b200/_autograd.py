@@ -10,10 +10,13 @@ non-torch nodes are two ``torch.autograd.Function`` s around the CUDA kernels:
 * one synthesis level, whose adjoint is one zero-extension analysis level with the flipped
   reconstruction filters.
 
-The boundary extension itself (reflect / constant / periodic / symmetric) is applied beforehand with
-differentiable torch indexing, so its adjoint (the fold of the halo back into the signal) is torch's;
-because ``pad_left = L - 2`` is even, the level outputs are the slice ``[pad_left/2 : pad_left/2 + M]``
-of the zero-extension transform of the explicitly extended signal.
+The boundary extension (reflect / constant / periodic / symmetric) happens INSIDE the analysis kernel on the forward
+pass (``ModeLevelAnalysis``: no padded copy of the level input is made).  Because ``pad_left = L - 2`` is even, the
+level outputs are the slice ``[pad_left/2 : pad_left/2 + M]`` of the zero-extension transform ``A0`` of the extended
+signal ``E x``, so the backward pass is ``E^T A0^T S^T``: the band gradients are placed in a zero field (``S^T``), one
+synthesis launch with the flipped decomposition filters gives the gradient of the extended signal (``A0^T``), and
+``fold_extension`` adds every halo sample back onto the sample it was copied from (``E^T``; the source-index map is taken
+from the forward extension itself, so every mode, including extensions longer than the signal, folds consistently).
 
 Gradients with respect to the filter taps (learnable wavelets: the reference's filters are ``nn.Parameter`` s,
 ``src/ptwt/wavelets_learnable.py:167-189``, used by ``examples/network_compression/wavelet_linear.py:118,150``):
@@ -68,6 +71,44 @@ def extend(x: torch.Tensor, ndim: int, filt_len: int, mode: str) -> torch.Tensor
     for l, r in reversed(pads):
         flat += [l, r]
     return F.pad(x.unsqueeze(1), flat, mode=_TORCH_MODE[mode]).squeeze(1)
+
+
+_EXT_INDEX_CACHE: dict = {}
+
+
+def _ext_source_index(n: int, filt_len: int, mode: str, device: torch.device) -> torch.Tensor:
+    """For every position of the extended axis, the index of the sample of ``[0, n)`` it is a copy of."""
+    key = (n, filt_len, mode, str(device))
+    idx = _EXT_INDEX_CACHE.get(key)
+    if idx is None:
+        src = torch.arange(n, dtype=torch.float64).unsqueeze(0)
+        idx = extend(src, 1, filt_len, mode)[0].round().to(torch.long).to(device)
+        if len(_EXT_INDEX_CACHE) > 256:
+            _EXT_INDEX_CACHE.clear()
+        _EXT_INDEX_CACHE[key] = idx
+    return idx
+
+
+def fold_extension(gxp: torch.Tensor, dims: Sequence[int], filt_len: int, mode: str) -> torch.Tensor:
+    """Adjoint of :func:`extend`: gradient of the extended ``[B, P1..PN]`` -> gradient of ``[B, d1..dN]``.
+
+    The extension is separable, so the fold runs axis by axis: the interior is taken as is, every halo sample is
+    added onto its source sample (``index_add_``)."""
+    base = (2 * filt_len - 3) // 2
+    g = gxp
+    for a, n in enumerate(dims):
+        left, right = base, base + n % 2
+        ax = 1 + a
+        if g.shape[ax] != n + left + right:
+            raise AssertionError("fold_extension: unexpected extended length")
+        idx = _ext_source_index(n, filt_len, mode, g.device)
+        out = g.narrow(ax, left, n).clone()
+        if left:
+            out.index_add_(ax, idx[:left], g.narrow(ax, 0, left))
+        if right:
+            out.index_add_(ax, idx[left + n:], g.narrow(ax, left + n, right))
+        g = out
+    return g
 
 
 def _as_tap_tensor(seq, like: torch.Tensor) -> torch.Tensor:
@@ -180,31 +221,84 @@ class ZeroLevelAnalysis(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *grads):
-        from . import fwt
-
-        dec_lo, dec_hi = ctx.taps
-        ndim = ctx.ndim
         ref = next(g for g in grads if g is not None)
         bands = [g.contiguous() if g is not None else torch.zeros_like(ref) for g in grads]
-        gx = None
-        if ctx.needs_input_grad[0]:
-            # adjoint of (zero pad -> stride-2 correlation) = transposed convolution with the same kernel,
-            # cropped by the pad: the synthesis kernel with rec := flipped dec
-            wav = (None, None, list(dec_lo)[::-1], list(dec_hi)[::-1])
-            f = fwt.Fold(ndim, tuple(range(-ndim, 0)), list(ctx.in_shape))
-            gx = fwt._synthesis(bands[0], [list(bands[1:])], [bands[1]], wav, ndim, f)
-            sl = (slice(None),) + tuple(slice(0, n) for n in ctx.in_shape[1:])
-            gx = gx[sl]
-        g_lo = g_hi = None
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            (x,) = ctx.saved_tensors
-            d = _tap_grads(bands, x, ndim, dec_lo, dec_hi, synthesis=False).flip(1)   # d dec[m] = out[L - 1 - m]
-            ldt, ldev, lshape, hdt, hdev, hshape = ctx.tap_meta
-            if ctx.needs_input_grad[1]:
-                g_lo = d[0].to(device=ldev, dtype=ldt).reshape(lshape)
-            if ctx.needs_input_grad[2]:
-                g_hi = d[1].to(device=hdev, dtype=hdt).reshape(hshape)
+        x = ctx.saved_tensors[0] if (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) else None
+        gx, g_lo, g_hi = _zero_analysis_backward(bands, ctx.in_shape, ctx.taps, ctx.ndim, ctx.tap_meta, x,
+                                                 ctx.needs_input_grad[:3])
         return gx, g_lo, g_hi, None
+
+
+def _zero_analysis_backward(bands, in_shape, taps, ndim: int, tap_meta, x, needs):
+    """Backward of one zero-extension analysis level of a signal of shape ``in_shape``: (gx, g_dec_lo, g_dec_hi)."""
+    from . import fwt
+
+    dec_lo, dec_hi = taps
+    gx = None
+    if needs[0]:
+        # adjoint of (zero pad -> stride-2 correlation) = transposed convolution with the same kernel,
+        # cropped by the pad: the synthesis kernel with rec := flipped dec
+        wav = (None, None, list(dec_lo)[::-1], list(dec_hi)[::-1])
+        f = fwt.Fold(ndim, tuple(range(-ndim, 0)), list(in_shape))
+        gx = fwt._synthesis(bands[0], [list(bands[1:])], [bands[1]], wav, ndim, f)
+        sl = (slice(None),) + tuple(slice(0, n) for n in in_shape[1:])
+        gx = gx[sl]
+    g_lo = g_hi = None
+    if needs[1] or needs[2]:
+        d = _tap_grads(bands, x, ndim, dec_lo, dec_hi, synthesis=False).flip(1)   # d dec[m] = out[L - 1 - m]
+        ldt, ldev, lshape, hdt, hdev, hshape = tap_meta
+        if needs[1]:
+            g_lo = d[0].to(device=ldev, dtype=ldt).reshape(lshape)
+        if needs[2]:
+            g_hi = d[1].to(device=hdev, dtype=hdt).reshape(hshape)
+    return gx, g_lo, g_hi
+
+
+class ModeLevelAnalysis(torch.autograd.Function):
+    """One analysis level with the boundary extension of ``mode`` evaluated inside the kernel (no padded copy of the
+    input); backward = fold(synthesis(band gradients in a zero field)), see the module docstring."""
+
+    @staticmethod
+    def forward(ctx, x, dec_lo_t, dec_hi_t, ndim: int, mode: str):
+        from . import fwt
+
+        dec_lo, dec_hi = _floats(dec_lo_t), _floats(dec_hi_t)
+        wav = (list(dec_lo), list(dec_hi), list(dec_lo), list(dec_hi))
+        approx, details, _ = fwt._analysis(x, wav, mode, 1, None, ndim)
+        ctx.taps = (dec_lo, dec_hi)
+        ctx.ndim = ndim
+        ctx.mode = mode
+        ctx.in_shape = tuple(x.shape)
+        ctx.tap_meta = (dec_lo_t.dtype, dec_lo_t.device, tuple(dec_lo_t.shape), dec_hi_t.dtype, dec_hi_t.device,
+                        tuple(dec_hi_t.shape))
+        ctx.save_for_backward(x if (dec_lo_t.requires_grad or dec_hi_t.requires_grad) else None)
+        return (approx,) + tuple(details[0])
+
+    @staticmethod
+    def backward(ctx, *grads):
+        from . import _native as N
+
+        ndim, mode = ctx.ndim, ctx.mode
+        L = len(ctx.taps[0])
+        dims = ctx.in_shape[1:]
+        base = (2 * L - 3) // 2
+        shift = base // 2
+        ext_dims = tuple(n + 2 * base + n % 2 for n in dims)
+        ref = next(g for g in grads if g is not None)
+        m = tuple(ref.shape[1:])
+        # S^T: the band gradients inside the zero field of the zero-extension transform of the extended signal
+        flat: list[int] = []
+        for a in reversed(range(ndim)):
+            mp = N.coeff_len(ext_dims[a], L)
+            flat += [shift, mp - m[a] - shift]
+        bands = [F.pad(g if g is not None else torch.zeros_like(ref), flat) for g in grads]
+        xp = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            xp = extend(ctx.saved_tensors[0], ndim, L, mode)   # recomputed here instead of kept from the forward pass
+        gxp, g_lo, g_hi = _zero_analysis_backward(bands, (ctx.in_shape[0],) + ext_dims, ctx.taps, ndim, ctx.tap_meta, xp,
+                                                  ctx.needs_input_grad[:3])
+        gx = fold_extension(gxp, dims, L, mode) if gxp is not None else None
+        return gx, g_lo, g_hi, None, None
 
 
 class LevelSynthesis(torch.autograd.Function):
@@ -265,17 +359,17 @@ def analysis_with_grad(x: torch.Tensor, dec_lo, dec_hi, mode: str, level: int, n
         raise NotImplementedError("the differentiable path needs an even filter length")
     home = x.device
     cur = x.to(dev)
-    shift = ((2 * L - 3) // 2) // 2
     details = []
     for _ in range(level):
         dims = tuple(cur.shape[1:])
         check_pad_feasible(mode, dims, L)
         m = tuple(N.coeff_len(n, L) for n in dims)
-        xp = cur if mode == "zero" else extend(cur, ndim, L, mode)
-        bands = ZeroLevelAnalysis.apply(xp, lo_t, hi_t, ndim)
-        if mode != "zero":
-            sl = (slice(None),) + tuple(slice(shift, shift + mm) for mm in m)
-            bands = tuple(b[sl] for b in bands)
+        if mode == "zero":
+            bands = ZeroLevelAnalysis.apply(cur, lo_t, hi_t, ndim)
+        else:
+            bands = ModeLevelAnalysis.apply(cur, lo_t, hi_t, ndim, mode)
+        if tuple(bands[0].shape[1:]) != m:
+            raise AssertionError("unexpected coefficient extents")
         details.append([b.to(home) for b in bands[1:]])
         cur = bands[0]
     details.reverse()

@@ -456,6 +456,32 @@ def test_filter_tap_gradients_match_the_reference_operators(mode):
             assert_close_rel(ta.grad, tb.grad, scale=scale, what=f"{name} grad of {fwd.__name__} {mode}")
 
 
+@pytest.mark.parametrize("mode", ["constant", "symmetric", "periodic", "reflect"])
+def test_autograd_extension_longer_than_the_signal(mode):
+    """Under grad the boundary extension runs inside the analysis kernel and the backward pass folds the gradient of
+    the extended signal (ModeLevelAnalysis): short signals whose extension wraps more than once, odd lengths, all the
+    levels the signal allows -- data and filter gradients against the oracle's torch-operator chain."""
+    g = torch.Generator().manual_seed(47)
+    for n, wav, level in ((9, "db4", 1), (11, "db3", 2), (6, "db2", 1), (23, "db5", 1)):
+        x = torch.randn(3, n, generator=g, dtype=torch.float64)
+        wa, wb = _learnable(wav), _learnable(wav)
+        xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        try:
+            cb = P.wavedec(xb, wb, mode=mode, level=level)
+        except (RuntimeError, ValueError):    # torch's pad refuses this mode at this length: so does the reference
+            with pytest.raises((RuntimeError, ValueError)):
+                wt.wavedec(xa.to(DEV), wa, mode=mode, level=level)
+            continue
+        ca = wt.wavedec(xa.to(DEV), wa, mode=mode, level=level)
+        for a, b in zip(ca, cb):
+            assert_close_rel(a, b, scale=float(b.abs().max()) + 1.0, what=f"short signal forward {mode} n={n}")
+        _weighted_sum(ca, 5).backward()
+        _weighted_sum(cb, 5).backward()
+        assert_close_rel(xa.grad, xb.grad, scale=float(xb.grad.abs().max()), what=f"short signal data grad {mode} n={n}")
+        for ta, tb in zip(wa[:2], wb[:2]):
+            assert_close_rel(ta.grad, tb.grad, scale=float(tb.grad.abs().max()), what=f"short signal tap grad {mode} n={n}")
+
+
 def test_filter_tap_gradients_first_layer_and_float32():
     """Data without grad, filters with grad (the usual first-layer case): the filters still get their gradient; float32
     filters on the GPU get float32 gradients on the GPU."""

@@ -294,3 +294,28 @@ def test_install_leaves_a_cpu_only_machine_alone():
     assert ptwt.wavedec is before and ptwt.packets.wavedec is before
     c = ptwt.wavedec(torch.arange(16.0), "haar", mode="zero", level=2)
     assert [t.shape[-1] for t in c] == [4, 4, 8]
+
+
+def test_fold_extension_is_the_adjoint_of_the_boundary_extension():
+    """The differentiable path extends inside the kernel on the forward pass and folds the gradient of the extended
+    signal back on the backward pass (_autograd.fold_extension).  Pure torch, so checked here against autograd of the
+    extension itself: every mode, 1-D .. 3-D, even / odd lengths, extensions longer than the signal."""
+    import torch
+    from pytorch_wavelet_toolbox_b200._autograd import extend, fold_extension
+
+    g = torch.Generator().manual_seed(5)
+    checked = 0
+    for mode in ("reflect", "constant", "periodic", "symmetric"):
+        for filt_len in (2, 4, 8, 12):
+            for dims in ((5,), (7,), (8,), (33,), (5, 6), (16, 9), (4, 5, 6), (13, 8, 7)):
+                x = torch.randn((2,) + dims, generator=g, dtype=torch.float64, requires_grad=True)
+                try:
+                    xp = extend(x, len(dims), filt_len, mode)
+                except RuntimeError:          # torch refuses reflect / circular pads longer than the signal
+                    continue
+                gy = torch.randn(xp.shape, generator=g, dtype=torch.float64)
+                (want,) = torch.autograd.grad(xp, x, gy)
+                got = fold_extension(gy, dims, filt_len, mode)
+                assert got.shape == want.shape and float((got - want).abs().max()) < 1e-12, (mode, filt_len, dims)
+                checked += 1
+    assert checked > 80
