@@ -39,7 +39,7 @@ CONFIGS = {
             kernel="fwd3d_tile_kernel<8> (level-1 launch)", kernel_level=1),
     4: dict(kind="matrix", wavelet="db6", level=None, mode="zero", shape=(1024, 65536), dtype="f64", cpu_batch=16,
             metric="Msamples/s, MatrixWavedec db6 65536 fp64 (forward)", baseline_cfg="BASELINE.json configs[3]",
-            kernel="mat_fwd_dmma_kernel<12,128> (FP64 tensor cores; first group of 2 levels)", kernel_level=2),
+            kernel="mat_fwd_dmma2_kernel<12,128> (FP64 tensor cores; first launch = levels 1 + 2)", kernel_level=2),
     5: dict(kind="2d", wavelet="db8", level=5, mode="reflect", shape=(512, 2048, 2048), dtype="f32", cpu_batch=8,
             metric="Msamples/s, wavedec2 db8 L5 2048x2048 fp32 (forward)", baseline_cfg="BASELINE.json configs[4]",
             kernel="fwd2d_strip_f32_kernel<16,64,TMA> (level-1 launch)", kernel_level=1),
