@@ -73,3 +73,29 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert rc == -4
     with pytest.raises(_native.NativeError):
         _native.check(rc, "wt_dwt_fwd")
+
+
+def test_knob_registry_round_trips_and_rejects_unknown_names():
+    """The tuning / test switches (csrc/knobs.cuh) are process state of the library, set through the C ABI: every
+    name the source lists is accepted, set / get / unset round-trip, negative values survive (MATI_ROWS < 0 is
+    meaningful), unknown names fail with WT_EINVAL instead of being silently ignored."""
+    from pytorch_wavelet_toolbox_b200 import _native
+
+    text = (ROOT / "pytorch_wavelet_toolbox_b200" / "csrc" / "knobs.cuh").read_text()
+    body = text[text.index("#define WTB_KNOB_LIST(X)"):text.index("enum KnobId")]
+    names = re.findall(r"X\(([A-Z0-9_]+)\)", body)
+    assert len(names) >= 30 and len(names) == len(set(names))
+    for must in ("NO_DMMA", "MATF_VARIANT", "MATI_ROWS", "MATI_K", "MATF_K", "WPAIR", "DISABLE_FUSED"):
+        assert must in names
+    for name in names:
+        before = _native.get_knob(name)
+        with _native.knobs(**{name: -3}):
+            assert _native.get_knob(name) == -3
+            with _native.knobs(**{name: None}):
+                assert _native.get_knob(name) is None
+            assert _native.get_knob(name) == -3
+        assert _native.get_knob(name) == before
+    with pytest.raises(Exception):
+        _native.set_knob("NOT_A_KNOB", 1)
+    with pytest.raises(Exception):
+        _native.get_knob("NOT_A_KNOB")
